@@ -1,0 +1,356 @@
+// Ray-side kernels of the hot path:
+//   * postprocess_kernel        — 1:1 with common.cu:129-149 (pack kaolin nuggets into a padded [N,I,2])
+//   * interval_walk_kernel      — 1:1 with common.cu:41-105 (cumulative occupied length -> z), never spins
+//   * ray_march_kernel          — fused replacement of OctreeManager.ray_trace (Utils.py:443-475, kaolin trace +
+//                                 postprocess) + sample_rays_uniform_occupied_voxels (nerf_runner.py:979-1011)
+//                                 + around-depth samples (nerf_runner.py:1063-1081): one warp per ray, DDA through a
+//                                 dense (2^level)^3 occupancy bitmask held in shared memory, intervals kept in
+//                                 shared memory, samples produced by all 32 lanes. No host sync, no [N,I,2] round
+//                                 trip through HBM unless the caller asks for the tap.
+// All float arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) so it is reproducible
+// operation-for-operation by the numpy oracle.
+#include "nof_common.cuh"
+
+namespace nof {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void postprocess_kernel(const int64_t* __restrict__ ray_index, const float* __restrict__ depth_in_out,
+                                   const int64_t* __restrict__ unique_ids, const int64_t* __restrict__ start_poss, int M,
+                                   int U, int max_inter, int n_rays, float* __restrict__ out) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  const int64_t i_ray = unique_ids[u];
+  if (i_ray < 0 || i_ray >= n_rays) return;
+  float* dst = out + (size_t)i_ray * max_inter * 2;
+  int k = 0;
+  for (int64_t i = start_poss[u]; i < M; ++i) {
+    if (ray_index[i] != i_ray) break;
+    const float a = depth_in_out[2 * i], b = depth_in_out[2 * i + 1];
+    if (a == 0.f || b == 0.f) break;
+    if (a > b) continue;
+    if ((double)fabsf(__fsub_rn(b, a)) < 1e-4) continue;
+    if (k >= max_inter) break;                 // the reference would write out of bounds here
+    dst[2 * k] = a;
+    dst[2 * k + 1] = b;
+    ++k;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Walk one sample through an interval list held anywhere addressable. Returns z; sets *err on inconsistency.
+template <typename IoPtr>
+__device__ __forceinline__ float walk_intervals(IoPtr io, int I, float rem, bool* err) {
+  const float eps = 1e-4f;
+  int k = 0;
+  while (true) {
+    if (k >= I) {
+      if (!(rem <= eps)) *err = true;
+      return io[2 * (I - 1) + 1];
+    }
+    const float a = io[2 * k];
+    if (a == 0.f) {
+      if (!(rem <= eps && k >= 1)) *err = true;
+      return k >= 1 ? io[2 * (k - 1) + 1] : 0.f;
+    }
+    const float len = __fsub_rn(io[2 * k + 1], a);
+    if (rem <= len) return __fadd_rn(a, rem);
+    rem = __fsub_rn(rem, len);
+    ++k;
+  }
+}
+
+// x = sample (fastest, coalesced), y = ray — the reference maps x to rays (uncoalesced, common.cu:116-122).
+__global__ void interval_walk_kernel(const float* __restrict__ z_in_out, const float* __restrict__ z_sampled,
+                                     float* __restrict__ z_vals, int N, int I, int S, int32_t* err_flag) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (s >= S || r >= N) return;
+  const float* io = z_in_out + (size_t)r * I * 2;
+  if (io[0] == 0.f) return;                    // common.cu:54
+  bool err = false;
+  const float z = walk_intervals(io, I, z_sampled[(size_t)r * S + s], &err);
+  z_vals[(size_t)r * S + s] = z;
+  if (err && err_flag) atomicExch(err_flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// torch.linspace(0,1,S) as its CUDA kernel evaluates it (step=(end-start)/(steps-1); lower half start+step*i,
+// upper half end-step*(steps-i-1), each contracted to one FMA).
+__device__ __forceinline__ float linspace01(int i, int S) {
+  if (S == 1) return 0.f;
+  const float step = __fdiv_rn(1.0f, (float)(S - 1));
+  return (i < S / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(S - i - 1), 1.0f);
+}
+
+// sample_rays_uniform (nerf_runner.py:67-87) for one (ray, sample): stratified value in [near, far].
+__device__ __forceinline__ float stratified(int i, int S, float nearv, float farv, bool perturb, float u) {
+  auto zlin = [&](int j) {
+    const float t = linspace01(j, S);
+    return __fadd_rn(__fmul_rn(nearv, __fsub_rn(1.f, t)), __fmul_rn(farv, t));
+  };
+  float z = zlin(i);
+  if (perturb) {
+    const float lower = (i == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, zlin(i - 1)));
+    const float upper = (i == S - 1) ? z : __fmul_rn(0.5f, __fadd_rn(zlin(i + 1), z));
+    z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u));
+    z = fminf(fmaxf(z, nearv), farv);
+  }
+  return z;
+}
+
+constexpr int MARCH_WARPS = 8;
+
+__global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg cfg, const float* __restrict__ rays,
+                                                                     const float* __restrict__ tf,
+                                                                     const uint32_t* __restrict__ occ_bits,
+                                                                     const float* __restrict__ t_rand,
+                                                                     float* __restrict__ z_vals,
+                                                                     float* __restrict__ intervals_out,
+                                                                     int32_t* err_flag) {
+  extern __shared__ uint32_t smem_u32[];
+  const int n = 1 << cfg.level;
+  const int occ_words = (n * n * n + 31) / 32;
+  uint32_t* s_occ = smem_u32;
+  float* s_io_all = reinterpret_cast<float*>(smem_u32 + occ_words);
+  for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s_occ[i] = occ_bits[i];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int I = cfg.I_max;
+  float* io_t = s_io_all + (size_t)warp * I * 4;       // travel-time intervals
+  float* io_z = io_t + (size_t)I * 2;                  // z intervals (scaled, clipped)
+  const int S = cfg.S_occ + cfg.S_depth;
+
+  for (int r = blockIdx.x * MARCH_WARPS + warp; r < cfg.N; r += gridDim.x * MARCH_WARPS) {
+    const float* row = rays + (size_t)r * cfg.ray_dim;
+    const float dx = row[0], dy = row[1], dz = row[2];
+    const float depth = row[6];
+    const int frame = (int)row[8];
+    const float* T = tf + (size_t)frame * 12;
+    // unit camera-frame direction, world origin and world direction (nerf_runner.py:1045-1057)
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float ux = __fdiv_rn(dx, nrm), uy = __fdiv_rn(dy, nrm), uz = __fdiv_rn(dz, nrm);
+    float o[3], d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      o[a] = T[a * 4 + 3];
+      d[a] = __fadd_rn(__fadd_rn(__fmul_rn(T[a * 4 + 0], ux), __fmul_rn(T[a * 4 + 1], uy)), __fmul_rn(T[a * 4 + 2], uz));
+    }
+    int count = 0;
+    bool overflow = false;
+    if (lane == 0) {
+      // ---- voxel DDA (replaces kaolin unbatched_raytrace; packing rule of common.cu:137-148 applied on the fly)
+      float inv[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) inv[a] = __fdiv_rn(1.0f, d[a]);
+      float t0 = 0.f, t1 = __int_as_float(0x7f800000);
+      bool hit = true;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (d[a] == 0.f) {
+          if (o[a] < -1.f || o[a] > 1.f) hit = false;
+        } else {
+          const float ta = __fmul_rn(__fsub_rn(-1.f, o[a]), inv[a]);
+          const float tb = __fmul_rn(__fsub_rn(1.f, o[a]), inv[a]);
+          t0 = fmaxf(t0, fminf(ta, tb));
+          t1 = fminf(t1, fmaxf(ta, tb));
+        }
+      }
+      if (hit && t0 < t1) {
+        const float cell = __fdiv_rn(2.0f, (float)n);
+        int ix[3], step[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float p = __fadd_rn(o[a], __fmul_rn(t0, d[a]));
+          int c = (int)floorf(__fdiv_rn(__fadd_rn(p, 1.0f), cell));
+          ix[a] = min(max(c, 0), n - 1);
+          step[a] = d[a] > 0.f ? 1 : (d[a] < 0.f ? -1 : 0);
+        }
+        float t_in = t0;
+        bool stopped = false;                   // the packing rule's `break` (t_in==0 || t_out==0)
+        for (int guard = 0; guard < 3 * n + 3; ++guard) {
+          float t_out = __int_as_float(0x7f800000);
+          int ax = -1;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            if (step[a] != 0) {
+              const float plane = __fsub_rn(__fmul_rn((float)(ix[a] + (step[a] > 0 ? 1 : 0)), cell), 1.0f);
+              const float ta = __fmul_rn(__fsub_rn(plane, o[a]), inv[a]);
+              if (ta < t_out) { t_out = ta; ax = a; }
+            }
+          }
+          if (ax < 0) break;
+          t_out = fminf(t_out, t1);
+          const int cid = (ix[0] * n + ix[1]) * n + ix[2];
+          if (!stopped && ((s_occ[cid >> 5] >> (cid & 31)) & 1u)) {
+            if (t_in == 0.f || t_out == 0.f) {
+              stopped = true;
+            } else if (!(t_in > t_out) && !((double)fabsf(__fsub_rn(t_out, t_in)) < 1e-4)) {
+              if (count < I) {
+                io_t[2 * count] = t_in;
+                io_t[2 * count + 1] = t_out;
+                ++count;
+              } else {
+                overflow = true;
+              }
+            }
+          }
+          ix[ax] += step[ax];
+          if (ix[ax] < 0 || ix[ax] >= n || t_out >= t1) break;
+          t_in = t_out;
+        }
+      }
+    }
+    count = __shfl_sync(0xffffffffu, count, 0);
+    __syncwarp();
+    // ---- z intervals: t -> z (nerf_runner.py:987-990), clip to depth+trunc for valid-depth rays (:992-999)
+    const float absz = fabsf(uz);
+    const bool valid_depth = (depth >= cfg.near_sc) && (depth <= cfg.far_sc);
+    const float zmax = __fadd_rn(depth, cfg.trunc);
+    for (int k = lane; k < I; k += 32) {
+      float a = 0.f, b = 0.f;
+      if (k < count) {
+        a = __fmul_rn(io_t[2 * k], absz);
+        b = __fmul_rn(io_t[2 * k + 1], absz);
+      }
+      if (intervals_out) {
+        intervals_out[((size_t)r * I + k) * 2] = k < count ? io_t[2 * k] : 0.f;
+        intervals_out[((size_t)r * I + k) * 2 + 1] = k < count ? io_t[2 * k + 1] : 0.f;
+      }
+      io_t[2 * k] = a;                          // keep the unclipped z intervals for the invalid-depth branch
+      io_t[2 * k + 1] = b;
+      if (valid_depth && a > 0.f && b > 0.f) {
+        a = fminf(fmaxf(a, 0.f), zmax);
+        b = fminf(fmaxf(b, 0.f), zmax);
+      }
+      io_z[2 * k] = a;
+      io_z[2 * k + 1] = b;
+    }
+    __syncwarp();
+    // total occupied length, summed front to back (every lane redundantly; I is small)
+    float total = 0.f;
+    for (int k = 0; k < I; ++k) total = __fadd_rn(total, __fsub_rn(io_z[2 * k + 1], io_z[2 * k]));
+    bool err = false;
+    float* zrow = z_vals + (size_t)r * S;
+    const bool has_any = io_z[0] != 0.f;       // common.cu:54: rays without intervals keep z = 0
+    for (int s = lane; s < cfg.S_occ; s += 32) {
+      float u = 0.f;
+      if (cfg.perturb) {
+        if (t_rand) u = t_rand[(size_t)r * S + s];
+        else {
+          uint4 rnd = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)(s >> 2), (uint32_t)cfg.offset, (uint32_t)(cfg.offset >> 32)),
+                                    make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32)));
+          const uint32_t w = (s & 3) == 0 ? rnd.x : (s & 3) == 1 ? rnd.y : (s & 3) == 2 ? rnd.z : rnd.w;
+          u = u32_to_unit(w);
+        }
+      }
+      const float zc = stratified(s, cfg.S_occ, 0.f, total, cfg.perturb != 0, u);
+      zrow[s] = has_any ? walk_intervals(io_z, I, zc, &err) : 0.f;
+    }
+    // ---- around-depth samples (nerf_runner.py:1063-1081)
+    if (cfg.S_depth > 0) {
+      float total2 = 0.f;
+      if (!valid_depth) for (int k = 0; k < I; ++k) total2 = __fadd_rn(total2, __fsub_rn(io_t[2 * k + 1], io_t[2 * k]));
+      const float nd = __fsub_rn(depth, cfg.trunc);
+      const float fd = __fadd_rn(depth, __fmul_rn(cfg.trunc, cfg.neg_trunc_ratio));
+      for (int j = lane; j < cfg.S_depth; j += 32) {
+        const int s = cfg.S_occ + j;
+        float u = 0.f;
+        if (cfg.perturb) {
+          if (t_rand) u = t_rand[(size_t)r * S + s];
+          else {
+            uint4 rnd = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)(s >> 2), (uint32_t)cfg.offset, (uint32_t)(cfg.offset >> 32)),
+                                      make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32)));
+            const uint32_t w = (s & 3) == 0 ? rnd.x : (s & 3) == 1 ? rnd.y : (s & 3) == 2 ? rnd.z : rnd.w;
+            u = u32_to_unit(w);
+          }
+        }
+        float z;
+        if (valid_depth) {
+          z = stratified(j, cfg.S_depth, nd, fd, cfg.perturb != 0, u);
+        } else {                                 // second occupied-voxel sampling, unclipped (:1074-1076)
+          const float zc = stratified(j, cfg.S_depth, 0.f, total2, cfg.perturb != 0, u);
+          z = (io_t[0] != 0.f) ? walk_intervals(io_t, I, zc, &err) : 0.f;
+        }
+        zrow[s] = z;
+      }
+    }
+    if ((err || (lane == 0 && overflow)) && err_flag) atomicExch(err_flag, 1);
+    __syncwarp();
+  }
+}
+
+__global__ void gather_rays_kernel(const float* __restrict__ pool, const int64_t* __restrict__ ids, float* __restrict__ batch,
+                                   int N, int ray_dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * ray_dim) return;
+  const int r = i / ray_dim, c = i - r * ray_dim;
+  batch[i] = __ldg(pool + (size_t)ids[r] * ray_dim + c);
+}
+
+}  // namespace nof
+
+using namespace nof;
+
+extern "C" int nof_sample_rays_uniform_occupied_voxels(const float* z_in_out, const float* z_sampled, float* z_vals, int N,
+                                                       int I, int S, int32_t* err_flag, nof_stream_t stream) {
+  NOF_REQUIRE(z_in_out && z_sampled && z_vals, "nof_sample_rays_uniform_occupied_voxels: null pointer");
+  NOF_REQUIRE(N >= 0 && I >= 1 && S >= 0, "nof_sample_rays_uniform_occupied_voxels: bad sizes N=%d I=%d S=%d", N, I, S);
+  if (N == 0 || S == 0) return NOF_OK;
+  NOF_REQUIRE(N <= 65535 * 1024, "nof_sample_rays_uniform_occupied_voxels: N too large");
+  // grid.y is limited to 65535: fold rays beyond that into multiple launches
+  for (int r0 = 0; r0 < N; r0 += 65535) {
+    const int n = min(65535, N - r0);
+    dim3 grid(div_up(S, 128), n);
+    interval_walk_kernel<<<grid, 128, 0, as_stream(stream)>>>(z_in_out + (size_t)r0 * I * 2, z_sampled + (size_t)r0 * S,
+                                                               z_vals + (size_t)r0 * S, n, I, S, err_flag);
+  }
+  return check_launch("interval_walk_kernel");
+}
+
+extern "C" int nof_postprocess_octree_ray_tracing(const int64_t* ray_index, const float* depth_in_out,
+                                                  const int64_t* unique_ids, const int64_t* start_poss, int M, int U,
+                                                  int max_intersections, int N_rays, float* out, nof_stream_t stream) {
+  NOF_REQUIRE(out, "nof_postprocess_octree_ray_tracing: null output");
+  NOF_REQUIRE(max_intersections >= 1 && N_rays >= 0 && M >= 0 && U >= 0, "nof_postprocess_octree_ray_tracing: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(out, 0, (size_t)N_rays * max_intersections * 2 * sizeof(float), st);
+  if (U == 0 || M == 0) return check_launch("postprocess memset");
+  NOF_REQUIRE(ray_index && depth_in_out && unique_ids && start_poss, "nof_postprocess_octree_ray_tracing: null pointer");
+  postprocess_kernel<<<div_up(U, 256), 256, 0, st>>>(ray_index, depth_in_out, unique_ids, start_poss, M, U, max_intersections,
+                                                     N_rays, out);
+  return check_launch("postprocess_kernel");
+}
+
+extern "C" int nof_ray_march(const NofMarchCfg* cfg, const float* rays, const float* tf, const uint32_t* occ_bits,
+                             const float* t_rand, float* z_vals, float* intervals_out, int32_t* err_flag,
+                             nof_stream_t stream) {
+  NOF_REQUIRE(cfg && rays && tf && occ_bits && z_vals, "nof_ray_march: null pointer");
+  NOF_REQUIRE(cfg->level >= 0 && cfg->level <= 6, "nof_ray_march: level=%d unsupported (0..6)", cfg->level);
+  NOF_REQUIRE(cfg->I_max >= 1 && cfg->I_max <= 256, "nof_ray_march: I_max=%d out of range", cfg->I_max);
+  NOF_REQUIRE(cfg->ray_dim >= 9, "nof_ray_march: ray_dim=%d too small", cfg->ray_dim);
+  NOF_REQUIRE(cfg->S_occ >= 1 && cfg->S_depth >= 0, "nof_ray_march: bad sample counts");
+  if (cfg->N == 0) return NOF_OK;
+  const int n = 1 << cfg->level;
+  const size_t smem = (size_t)((n * n * n + 31) / 32) * 4 + (size_t)MARCH_WARPS * cfg->I_max * 4 * sizeof(float);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaFuncSetAttribute(ray_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
+  NOF_REQUIRE(smem <= 100 * 1024, "nof_ray_march: shared memory %zu too large", smem);
+  int sms = 148;
+  nof_device_info(&sms, nullptr);
+  const int blocks = min(div_up(cfg->N, MARCH_WARPS), sms * 4);
+  ray_march_kernel<<<blocks, MARCH_WARPS * 32, smem, as_stream(stream)>>>(*cfg, rays, tf, occ_bits, t_rand, z_vals,
+                                                                          intervals_out, err_flag);
+  return check_launch("ray_march_kernel");
+}
+
+extern "C" int nof_gather_rays(const float* pool, const int64_t* ids, float* batch, int N, int ray_dim, nof_stream_t stream) {
+  NOF_REQUIRE(pool && ids && batch, "nof_gather_rays: null pointer");
+  NOF_REQUIRE(N >= 0 && ray_dim >= 1, "nof_gather_rays: bad sizes");
+  if (N == 0) return NOF_OK;
+  gather_rays_kernel<<<div_up(N * ray_dim, 256), 256, 0, as_stream(stream)>>>(pool, ids, batch, N, ray_dim);
+  return check_launch("gather_rays_kernel");
+}

@@ -1,0 +1,784 @@
+// Fused forward + loss + backward of one Neural-Object-Field train step, AMP policy (cfg amp: true):
+// fp16 hash table gathered with 4-byte vector loads, fp16 activations resident in shared memory, the five tiny
+// dense layers of NeRFSmall (nerf_helpers.py:243-321) on tensor cores (mma.sync m16n8k16, fp32 accumulate) for
+// forward, dgrad and wgrad, weight gradients accumulated in registers across all tiles of a persistent CTA, fp32
+// vector reductions (red.global.add.v2.f32) for the grid gradient. Weights and biases are staged into shared
+// memory once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier).
+//
+// Replaces, for one batch: run_network + raw2outputs + loss assembly + loss.backward() of the reference
+// (nerf_runner.py:1083-1088,1227-1304,1132-1169,679-758; grid.py:34-99; gridencoder.cu:107-365).
+#include "nof_step_common.cuh"
+
+namespace nof {
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core / ldmatrix / TMA primitives
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t r[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t r[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float c[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory plan (halfs unless noted). Row strides are K+8 halfs: ldmatrix rows stay 16-byte aligned and the 8
+// rows of an 8x8 tile fall into distinct 16-byte bank groups.
+// ------------------------------------------------------------------------------------------------
+constexpr int LD64 = 72;   // stride of 64-wide activations / weights
+constexpr int LD32 = 40;   // stride of 32-wide
+constexpr int LD16 = 24;   // stride of 16-wide
+
+struct SmemPlan {
+  // offsets in bytes
+  int w1, w2, w3, w4, w5, bias, x0, x1, xc, x3, x4, d_o, out, rays, lv, bar, total;
+  int ldx0;                // stride (halfs) of X0 / W1 (KE + 8)
+};
+
+__host__ __device__ inline SmemPlan make_plan(int T, int KE) {
+  SmemPlan s;
+  s.ldx0 = KE + 8;
+  int o = 0;
+  auto take = [&](int bytes) { int r = o; o += (bytes + 127) / 128 * 128; return r; };
+  s.w1 = take(64 * s.ldx0 * 2);
+  s.w2 = take(16 * LD64 * 2);
+  s.w3 = take(64 * LD32 * 2);
+  s.w4 = take(64 * LD64 * 2);
+  s.w5 = take(16 * LD64 * 2);
+  s.bias = take(216 * 4);                    // b1 64, b2 16, b3 64, b4 64, b5 8
+  s.x0 = take(T * s.ldx0 * 2);
+  s.x1 = take(T * LD64 * 2);
+  s.xc = take(T * LD32 * 2);
+  s.x3 = take(T * LD64 * 2);
+  s.x4 = take(T * LD64 * 2);
+  s.d_o = take(T * LD16 * 2);                // dOut (phase 5), later dH2 (phase 2)
+  s.out = take(T * 4 * 4);                   // fp32 [T][4]
+  s.rays = take(MAX_R * (int)sizeof(RayS));
+  s.lv = take((int)sizeof(LevelS));
+  s.bar = take(64);
+  s.total = o;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-level GEMM pieces on the warp's own 32 rows (2 m-tiles)
+// ------------------------------------------------------------------------------------------------
+// Y[32 x N] = A[32 x K] * W^T, W stored [N][K] (nn.Linear layout).  acc[mt][nt][4]
+template <int K, int N>
+__device__ __forceinline__ void warp_fwd(const __half* A, int lda, const __half* W, int ldw, float (*acc)[N / 8][4], int lane) {
+#pragma unroll
+  for (int ks = 0; ks < K / 16; ++ks) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+      ldsm_x4(a[mt], A + (size_t)(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * lda + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+    for (int np = 0; np < N / 16; ++np) {      // two n-tiles per ldmatrix.x4
+      uint32_t b[4];
+      ldsm_x4(b, W + (size_t)(np * 16 + (lane & 7) + (lane >> 4) * 8) * ldw + ks * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma16816(acc[mt][np * 2], a[mt], b[0], b[1]);
+        mma16816(acc[mt][np * 2 + 1], a[mt], b[2], b[3]);
+      }
+    }
+    if constexpr ((N / 8) % 2 == 1) {          // N == 8: single n-tile (x4 load reads 16 W rows; rows 8..15 exist, unused)
+      uint32_t b[4];
+      ldsm_x4(b, W + (size_t)((N / 16) * 16 + (lane & 7) + (lane >> 4) * 8) * ldw + ks * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) mma16816(acc[mt][N / 8 - 1], a[mt], b[0], b[1]);
+    }
+  }
+}
+
+// dX[32 x NI] = dY[32 x KO] * W, W stored [KO][NI] row-major (k = output index of the layer).
+template <int KO, int NI>
+__device__ __forceinline__ void warp_dgrad(const __half* dY, int ldy, const __half* W, int ldw, float (*acc)[NI / 8][4], int lane) {
+#pragma unroll
+  for (int ks = 0; ks < KO / 16; ++ks) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+      ldsm_x4(a[mt], dY + (size_t)(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ldy + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+    for (int np = 0; np < NI / 16; ++np) {
+      uint32_t b[4];
+      ldsm_x4_t(b, W + (size_t)(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ldw + np * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma16816(acc[mt][np * 2], a[mt], b[0], b[1]);
+        mma16816(acc[mt][np * 2 + 1], a[mt], b[2], b[3]);
+      }
+    }
+  }
+}
+
+// One wgrad unit: dW[strip*16 .. +16][nt0*8 .. +NTU*8] += dY^T X over all T rows of the CTA; bias via a ones B-operand.
+template <int NTU>
+__device__ __forceinline__ void wgrad_unit(const __half* dY, int ldy, const __half* X, int ldx, int T, int strip, int nt0,
+                                           float acc[4][4], float* bias2, bool do_bias, int lane) {
+  const uint32_t ones = 0x3C003C00u;
+  for (int ks = 0; ks < T / 16; ++ks) {
+    uint32_t a[4];
+    ldsm_x4_t(a, dY + (size_t)(ks * 16 + (lane & 7) + (lane >> 4) * 8) * ldy + strip * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+    for (int np = 0; np < NTU / 2; ++np) {
+      uint32_t b[4];
+      ldsm_x4_t(b, X + (size_t)(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ldx + (nt0 + np * 2) * 8 + (lane >> 4) * 8);
+      mma16816(acc[np * 2], a, b[0], b[1]);
+      mma16816(acc[np * 2 + 1], a, b[2], b[3]);
+    }
+    if (do_bias) {
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      mma16816(t, a, ones, ones);
+      bias2[0] += t[0];
+      bias2[1] += t[2];
+    }
+  }
+}
+
+// wgrad unit list: (layer, strip, n-tile group). Unit u -> warp u % NW, slot u / NW.
+//   L1: 4 strips x (KE/8 n-tiles, in groups of NTU1)   L2: 1 strip x 8 nt -> 2 groups of 4
+//   L3: 4 strips x 4 nt                               L4: 4 strips x 8 nt -> 8 units     L5: 1 strip x 8 nt -> 2 units
+struct UnitMap {
+  int l1, l2, l3, l4, l5, total;   // first unit id of each layer
+};
+__host__ __device__ constexpr UnitMap unit_map(int KE) {
+  UnitMap m{};
+  m.l1 = 0;
+  m.l2 = m.l1 + 4 * ((KE / 8 + 3) / 4);
+  m.l3 = m.l2 + 2;
+  m.l4 = m.l3 + 4;
+  m.l5 = m.l4 + 8;
+  m.total = m.l5 + 2;
+  return m;
+}
+constexpr int MAX_UNITS = 20;
+
+template <int NW>
+struct WgradAcc {
+  static constexpr int SLOTS = (MAX_UNITS + NW - 1) / NW;
+  float w[SLOTS][4][4];
+  float b[SLOTS][2];
+};
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int NW, int KE_>
+__global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(const StepArgs a) {
+  constexpr int T = NW * 32;
+  constexpr int KE = KE_;
+  constexpr int LDX0 = KE + 8;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemPlan sp = make_plan(T, KE);
+  __half* sW1 = reinterpret_cast<__half*>(smem + sp.w1);
+  __half* sW2 = reinterpret_cast<__half*>(smem + sp.w2);
+  __half* sW3 = reinterpret_cast<__half*>(smem + sp.w3);
+  __half* sW4 = reinterpret_cast<__half*>(smem + sp.w4);
+  __half* sW5 = reinterpret_cast<__half*>(smem + sp.w5);
+  float* sB = reinterpret_cast<float*>(smem + sp.bias);
+  __half* X0 = reinterpret_cast<__half*>(smem + sp.x0);
+  __half* X1 = reinterpret_cast<__half*>(smem + sp.x1);
+  __half* XC = reinterpret_cast<__half*>(smem + sp.xc);
+  __half* X3 = reinterpret_cast<__half*>(smem + sp.x3);
+  __half* X4 = reinterpret_cast<__half*>(smem + sp.x4);
+  __half* DO = reinterpret_cast<__half*>(smem + sp.d_o);
+  float* sOut = reinterpret_cast<float*>(smem + sp.out);
+  RayS* sRay = reinterpret_cast<RayS*>(smem + sp.rays);
+  LevelS& lv = *reinterpret_cast<LevelS*>(smem + sp.lv);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sp.bar);
+  float* sStage = reinterpret_cast<float*>(smem + sp.x1);     // fp32 staging of the packed params (aliases X1..)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int E = a.E, V = a.V, L = a.p.L;
+  const float scale_ls = a.p.loss_scale ? *a.p.loss_scale : 1.0f;
+  constexpr UnitMap um = unit_map(KE);
+
+  // ---- stage parameters: TMA bulk copy of the packed fp32 block into smem, then convert to padded fp16 tiles
+  const int n_par = a.po[9] + 3;
+  const uint32_t par_bytes = (uint32_t)((n_par * 4 + 15) / 16 * 16);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, par_bytes);
+    tma_bulk_g2s(sStage, a.p.mlp, par_bytes, bar);
+  }
+  init_levels(lv, a);
+  // zero the weight tiles (padding rows / columns must be exact zeros)
+  for (int i = tid; i < (sp.bias - sp.w1) / 4; i += T) reinterpret_cast<uint32_t*>(smem + sp.w1)[i] = 0u;
+  __syncthreads();
+  mbar_wait(bar, 0);
+  {
+    const float* P = sStage;
+    for (int i = tid; i < 64 * E; i += T) sW1[(i / E) * LDX0 + (i % E)] = __float2half_rn(P[a.po[0] + i]);
+    for (int i = tid; i < 16 * 64; i += T) sW2[(i / 64) * LD64 + (i % 64)] = __float2half_rn(P[a.po[2] + i]);
+    const int K3 = V + 15;
+    for (int i = tid; i < 64 * K3; i += T) sW3[(i / K3) * LD32 + (i % K3)] = __float2half_rn(P[a.po[4] + i]);
+    for (int i = tid; i < 64 * 64; i += T) sW4[(i / 64) * LD64 + (i % 64)] = __float2half_rn(P[a.po[6] + i]);
+    for (int i = tid; i < 3 * 64; i += T) sW5[(i / 64) * LD64 + (i % 64)] = __float2half_rn(P[a.po[8] + i]);
+    // biases: autocast rounds them to fp16 as well (F.linear casts all three operands)
+    for (int i = tid; i < 64; i += T) sB[i] = __half2float(__float2half_rn(P[a.po[1] + i]));
+    for (int i = tid; i < 16; i += T) sB[64 + i] = __half2float(__float2half_rn(P[a.po[3] + i]));
+    for (int i = tid; i < 64; i += T) sB[80 + i] = __half2float(__float2half_rn(P[a.po[5] + i]));
+    for (int i = tid; i < 64; i += T) sB[144 + i] = __half2float(__float2half_rn(P[a.po[7] + i]));
+    for (int i = tid; i < 8; i += T) sB[208 + i] = (i < 3) ? __half2float(__float2half_rn(P[a.po[9] + i])) : 0.f;
+  }
+  __syncthreads();
+
+  WgradAcc<NW> wg;
+#pragma unroll
+  for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wg.w[s][i][j] = 0.f;
+    wg.b[s][0] = wg.b[s][1] = 0.f;
+  }
+  float loss_acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float n_valid_s = 0.f, n_valid_r = 0.f;
+  bool overflow = false;
+
+  const int Sp = a.Sp, R = a.R, S = a.p.S;
+  const int rl = tid / Sp, sidx = tid - rl * Sp;
+  __half2* Jslot = reinterpret_cast<__half2*>(a.p.workspace) + (size_t)blockIdx.x * (MAX_L * 3) * T;
+  const int g8 = lane >> 2, t4 = lane & 3;
+
+  for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+    // ============ 1. ray setup
+    if (tid < R) setup_ray(sRay[tid], a, grp * R + tid);
+    __syncthreads();
+    const RayS& rs = sRay[rl];
+    const bool active = rs.active && sidx < S;
+    const float z = active ? a.p.z_vals[(size_t)rs.ray * S + sidx] : 0.f;
+    float pc[3], x[3], u[3];
+    world_point(rs, z, pc, x);
+    const bool valid = active && fabsf(x[0]) <= 1.f && fabsf(x[1]) <= 1.f && fabsf(x[2]) <= 1.f;   // nerf_runner.py:1245
+#pragma unroll
+    for (int d = 0; d < 3; ++d) u[d] = (x[d] + 1.0f) * 0.5f;                                        // grid.py:160
+    const float w_raw = active ? raw_weight(a, z, rs.depth) : 0.f;
+    {
+      const float ws = warp_sum(w_raw);
+      const unsigned anyv = __ballot_sync(0xffffffffu, valid);
+      if (lane == 0) {
+        if (ws != 0.f) atomicAdd(&sRay[rl].sumw, ws);
+        if (anyv) atomicOr(&sRay[rl].anyvalid, 1);
+      }
+    }
+    // ============ 2. colour-net input row (views part; geo filled by L2) and the multires gather
+    {
+      __half* xc = XC + (size_t)tid * LD32;
+#pragma unroll 4
+      for (int j = 0; j < KC; ++j) xc[j] = __float2half_rn(j < V ? rs.views[j] : 0.f);
+      __half* x0 = X0 + (size_t)tid * LDX0;
+      if (valid) {
+#pragma unroll 2
+        for (int l = 0; l < L; ++l) {
+          float enc[2], J[3][2];
+          if (a.p.need_pose_grad) {
+            gather_level<true, true>(a.p.table_f16, lv, l, u, enc, J);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) Jslot[(size_t)(l * 3 + d) * T + tid] = __floats2half2_rn(J[d][0], J[d][1]);
+          } else {
+            gather_level<true, false>(a.p.table_f16, lv, l, u, enc, J);
+          }
+          *reinterpret_cast<__half2*>(x0 + 2 * l) = __floats2half2_rn(enc[0], enc[1]);
+        }
+        for (int j = E; j < KE; ++j) x0[j] = __float2half_rn(0.f);
+      } else {
+        for (int j = 0; j < KE; j += 2) *reinterpret_cast<uint32_t*>(x0 + j) = 0u;   // nerf_runner.py:1247: zeros for invalid
+      }
+    }
+    __syncwarp();
+    // ============ 3. MLP forward on the warp's own 32 rows
+    const int row0 = warp * 32;
+    {
+      float acc[2][8][4];
+      // ---- L1: E -> 64, ReLU
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          acc[mt][nt][0] = sB[nt * 8 + 2 * t4]; acc[mt][nt][1] = sB[nt * 8 + 2 * t4 + 1];
+          acc[mt][nt][2] = acc[mt][nt][0];      acc[mt][nt][3] = acc[mt][nt][1];
+        }
+      warp_fwd<KE, 64>(X0 + (size_t)row0 * LDX0, LDX0, sW1, LDX0, acc, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          __half* y = X1 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
+          *reinterpret_cast<uint32_t*>(y) = pack_h2(fmaxf(acc[mt][nt][0], 0.f), fmaxf(acc[mt][nt][1], 0.f));
+          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(fmaxf(acc[mt][nt][2], 0.f), fmaxf(acc[mt][nt][3], 0.f));
+        }
+      __syncwarp();
+      // ---- L2: 64 -> 16 (sdf | geo 15), no activation
+      float acc2[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          acc2[mt][nt][0] = sB[64 + nt * 8 + 2 * t4]; acc2[mt][nt][1] = sB[64 + nt * 8 + 2 * t4 + 1];
+          acc2[mt][nt][2] = acc2[mt][nt][0];          acc2[mt][nt][3] = acc2[mt][nt][1];
+        }
+      warp_fwd<64, 16>(X1 + (size_t)row0 * LD64, LD64, sW2, LD64, acc2, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = row0 + mt * 16 + g8 + h * 8;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int col = nt * 8 + 2 * t4 + c;
+              const __half hv = __float2half_rn(acc2[mt][nt][h * 2 + c]);
+              if (col == 0) sOut[r * 4 + 3] = __half2float(hv);            // sdf (nerf_helpers.py:312)
+              else XC[(size_t)r * LD32 + V + col - 1] = hv;                 // geo feature -> colour-net input (:316)
+            }
+          }
+      __syncwarp();
+      // ---- L3: (V+15 padded 32) -> 64, ReLU
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          acc[mt][nt][0] = sB[80 + nt * 8 + 2 * t4]; acc[mt][nt][1] = sB[80 + nt * 8 + 2 * t4 + 1];
+          acc[mt][nt][2] = acc[mt][nt][0];           acc[mt][nt][3] = acc[mt][nt][1];
+        }
+      warp_fwd<KC, 64>(XC + (size_t)row0 * LD32, LD32, sW3, LD32, acc, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          __half* y = X3 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
+          *reinterpret_cast<uint32_t*>(y) = pack_h2(fmaxf(acc[mt][nt][0], 0.f), fmaxf(acc[mt][nt][1], 0.f));
+          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(fmaxf(acc[mt][nt][2], 0.f), fmaxf(acc[mt][nt][3], 0.f));
+        }
+      __syncwarp();
+      // ---- L4: 64 -> 64, ReLU
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          acc[mt][nt][0] = sB[144 + nt * 8 + 2 * t4]; acc[mt][nt][1] = sB[144 + nt * 8 + 2 * t4 + 1];
+          acc[mt][nt][2] = acc[mt][nt][0];            acc[mt][nt][3] = acc[mt][nt][1];
+        }
+      warp_fwd<64, 64>(X3 + (size_t)row0 * LD64, LD64, sW4, LD64, acc, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          __half* y = X4 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
+          *reinterpret_cast<uint32_t*>(y) = pack_h2(fmaxf(acc[mt][nt][0], 0.f), fmaxf(acc[mt][nt][1], 0.f));
+          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(fmaxf(acc[mt][nt][2], 0.f), fmaxf(acc[mt][nt][3], 0.f));
+        }
+      __syncwarp();
+      // ---- L5: 64 -> 3 (padded 8)
+      float acc5[2][1][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        acc5[mt][0][0] = sB[208 + 2 * t4]; acc5[mt][0][1] = sB[208 + 2 * t4 + 1];
+        acc5[mt][0][2] = acc5[mt][0][0];   acc5[mt][0][3] = acc5[mt][0][1];
+      }
+      warp_fwd<64, 8>(X4 + (size_t)row0 * LD64, LD64, sW5, LD64, acc5, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int col = 2 * t4 + c;
+            if (col < 3) sOut[(row0 + mt * 16 + g8 + h * 8) * 4 + col] = __half2float(__float2half_rn(acc5[mt][0][h * 2 + c]));
+          }
+    }
+    __syncthreads();                                        // (B) sumw / anyvalid complete, sOut rows visible
+    // ============ 4. compositing (nerf_runner.py:1163-1167)
+    float out4[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out4[c] = sOut[tid * 4 + c];
+    const float w = valid ? w_raw / (rs.sumw + 1e-10f) : 0.f;
+    {
+      float pr[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pr[c] = warp_sum(w * sigmoidf_(out4[c]));
+      if (lane == 0 && (pr[0] != 0.f || pr[1] != 0.f || pr[2] != 0.f)) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(&sRay[rl].rgb[c], pr[c]);
+      }
+    }
+    __syncthreads();                                        // (C) rgb_map complete
+    // ============ 5. loss seeds
+    const float ray_w = rs.ray_w_base * (rs.anyvalid ? 1.f : 0.f);
+    float d_out[4];
+    loss_seeds(a, rs, out4, z, w, valid, active ? ray_w : 0.f, d_out, loss_acc);
+    if (!active) { d_out[0] = d_out[1] = d_out[2] = d_out[3] = 0.f; }
+    if (valid) n_valid_s += 1.f;
+    if (sidx == 0 && rs.active) {
+      float e = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { const float dd = rs.rgb[c] - rs.gt[c]; e += dd * dd; }
+      loss_acc[1] += a.p.rgb_weight * e * ray_w * a.inv_N3;                     // nerf_runner.py:700-701
+      if (rs.anyvalid && rs.ray_w_base != 0.f) n_valid_r += 1.f;
+      if (a.p.rgb_map) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a.p.rgb_map[(size_t)rs.ray * 3 + c] = rs.rgb[c];
+      }
+    }
+    if (active) {
+      const size_t pi = (size_t)rs.ray * S + sidx;
+      if (a.p.raw) *reinterpret_cast<float4*>(a.p.raw + pi * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+      if (a.p.valid_samples) a.p.valid_samples[pi] = valid ? 1 : 0;
+      if (a.p.weights) a.p.weights[pi] = w;
+    }
+    float dsdf_s = d_out[3] * scale_ls;
+    {
+      float s0 = d_out[0] * scale_ls, s1 = d_out[1] * scale_ls, s2 = d_out[2] * scale_ls;
+      overflow |= !(fabsf(s0) <= 65504.f) || !(fabsf(s1) <= 65504.f) || !(fabsf(s2) <= 65504.f) || !(fabsf(dsdf_s) <= 65504.f);
+      __half* dr = DO + (size_t)tid * LD16;
+      *reinterpret_cast<uint32_t*>(dr) = pack_h2(s0, s1);
+      *reinterpret_cast<uint32_t*>(dr + 2) = pack_h2(s2, 0.f);
+#pragma unroll
+      for (int j = 4; j < 16; j += 2) *reinterpret_cast<uint32_t*>(dr + j) = 0u;
+    }
+    __syncthreads();                                        // (S0) dOut rows visible to every warp
+
+    // ============ 6. backward through the MLP
+    // ---- layer 5: wgrad (all rows) + dgrad (own rows) -> dY4 = dX4 * relu'(X4), in place
+#pragma unroll
+    for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
+      const int uid = s * NW + warp;
+      if (uid >= um.l5 && uid < um.total) wgrad_unit<4>(DO, LD16, X4, LD64, T, 0, (uid - um.l5) * 4, wg.w[s], wg.b[s], uid == um.l5, lane);
+    }
+    {
+      float acc[2][8][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+      warp_dgrad<16, 64>(DO + (size_t)row0 * LD16, LD16, sW5, LD64, acc, lane);
+      __syncthreads();                                      // every warp finished reading X4 (wgrad5)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          __half* y = X4 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
+          const __half2 m0 = *reinterpret_cast<__half2*>(y), m1 = *reinterpret_cast<__half2*>(y + 8 * LD64);
+          const float v0 = __low2float(m0) > 0.f ? acc[mt][nt][0] : 0.f, v1 = __high2float(m0) > 0.f ? acc[mt][nt][1] : 0.f;
+          const float v2 = __low2float(m1) > 0.f ? acc[mt][nt][2] : 0.f, v3 = __high2float(m1) > 0.f ? acc[mt][nt][3] : 0.f;
+          overflow |= !(fabsf(v0) <= 65504.f) || !(fabsf(v1) <= 65504.f) || !(fabsf(v2) <= 65504.f) || !(fabsf(v3) <= 65504.f);
+          *reinterpret_cast<uint32_t*>(y) = pack_h2(v0, v1);
+          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(v2, v3);
+        }
+    }
+    __syncthreads();                                        // dY4 visible
+    // ---- layer 4
+#pragma unroll
+    for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
+      const int uid = s * NW + warp;
+      if (uid >= um.l4 && uid < um.l5) {
+        const int k = uid - um.l4;
+        wgrad_unit<4>(X4, LD64, X3, LD64, T, k >> 1, (k & 1) * 4, wg.w[s], wg.b[s], (k & 1) == 0, lane);
+      }
+    }
+    {
+      float acc[2][8][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+      warp_dgrad<64, 64>(X4 + (size_t)row0 * LD64, LD64, sW4, LD64, acc, lane);
+      __syncthreads();                                      // wgrad4 finished reading X3
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          __half* y = X3 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
+          const __half2 m0 = *reinterpret_cast<__half2*>(y), m1 = *reinterpret_cast<__half2*>(y + 8 * LD64);
+          const float v0 = __low2float(m0) > 0.f ? acc[mt][nt][0] : 0.f, v1 = __high2float(m0) > 0.f ? acc[mt][nt][1] : 0.f;
+          const float v2 = __low2float(m1) > 0.f ? acc[mt][nt][2] : 0.f, v3 = __high2float(m1) > 0.f ? acc[mt][nt][3] : 0.f;
+          overflow |= !(fabsf(v0) <= 65504.f) || !(fabsf(v1) <= 65504.f) || !(fabsf(v2) <= 65504.f) || !(fabsf(v3) <= 65504.f);
+          *reinterpret_cast<uint32_t*>(y) = pack_h2(v0, v1);
+          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(v2, v3);
+        }
+    }
+    __syncthreads();                                        // dY3 visible
+    // ---- layer 3: wgrad (dY3^T XC), dgrad -> [dviews | dgeo]
+#pragma unroll
+    for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
+      const int uid = s * NW + warp;
+      if (uid >= um.l3 && uid < um.l4) wgrad_unit<4>(X3, LD64, XC, LD32, T, uid - um.l3, 0, wg.w[s], wg.b[s], true, lane);
+    }
+    {
+      float acc[2][4][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+      warp_dgrad<64, KC>(X3 + (size_t)row0 * LD64, LD64, sW3, LD32, acc, lane);
+      // dviews: sum over the 32 rows of this warp (all samples of one ray) — warp-level reduction, then one shared
+      // atomic per column per warp.
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = nt * 8 + 2 * t4 + c;
+          float v = acc[0][nt][c] + acc[0][nt][2 + c] + acc[1][nt][c] + acc[1][nt][2 + c];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (g8 == 0 && col < V && v != 0.f) atomicAdd(&sRay[rl].dviews[col], v);
+        }
+      // dH2 = [dsdf | dgeo] -> DO buffer (dOut is dead: wgrad5/dgrad5 completed before the barriers above)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int col = nt * 8 + 2 * t4 + c;
+              if (col >= V && col < V + 15) {
+                const float v = acc[mt][nt][h * 2 + c];
+                overflow |= !(fabsf(v) <= 65504.f);
+                DO[(size_t)(row0 + mt * 16 + g8 + h * 8) * LD16 + 1 + (col - V)] = __float2half_rn(v);
+              }
+            }
+      DO[(size_t)tid * LD16] = __float2half_rn(dsdf_s);
+    }
+    __syncthreads();                                        // dH2 visible
+    // ---- layer 2
+#pragma unroll
+    for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
+      const int uid = s * NW + warp;
+      if (uid >= um.l2 && uid < um.l3) wgrad_unit<4>(DO, LD16, X1, LD64, T, 0, (uid - um.l2) * 4, wg.w[s], wg.b[s], uid == um.l2, lane);
+    }
+    {
+      float acc[2][8][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+      warp_dgrad<16, 64>(DO + (size_t)row0 * LD16, LD16, sW2, LD64, acc, lane);
+      __syncthreads();                                      // wgrad2 finished reading X1
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          __half* y = X1 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
+          const __half2 m0 = *reinterpret_cast<__half2*>(y), m1 = *reinterpret_cast<__half2*>(y + 8 * LD64);
+          const float v0 = __low2float(m0) > 0.f ? acc[mt][nt][0] : 0.f, v1 = __high2float(m0) > 0.f ? acc[mt][nt][1] : 0.f;
+          const float v2 = __low2float(m1) > 0.f ? acc[mt][nt][2] : 0.f, v3 = __high2float(m1) > 0.f ? acc[mt][nt][3] : 0.f;
+          overflow |= !(fabsf(v0) <= 65504.f) || !(fabsf(v1) <= 65504.f) || !(fabsf(v2) <= 65504.f) || !(fabsf(v3) <= 65504.f);
+          *reinterpret_cast<uint32_t*>(y) = pack_h2(v0, v1);
+          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(v2, v3);
+        }
+    }
+    __syncthreads();                                        // dY1 visible
+    // ---- layer 1: wgrad (dY1^T X0), dgrad -> dEnc (fp32, scaled) into the X3 region (dead)
+    {
+      constexpr int NT1 = KE / 8;
+      constexpr int NTU1 = NT1 < 4 ? NT1 : 4;
+      constexpr int G1 = (NT1 + 3) / 4;                     // n-tile groups per strip
+#pragma unroll
+      for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
+        const int uid = s * NW + warp;
+        if (uid >= um.l1 && uid < um.l2) {
+          const int k = uid - um.l1;
+          wgrad_unit<NTU1>(X1, LD64, X0, LDX0, T, k / G1, (k % G1) * 4, wg.w[s], wg.b[s], (k % G1) == 0, lane);
+        }
+      }
+      float acc[2][NT1][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT1; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+      warp_dgrad<64, KE>(X1 + (size_t)row0 * LD64, LD64, sW1, LDX0, acc, lane);
+      float* dE = reinterpret_cast<float*>(X3);             // [T][36] fp32 (144-byte rows)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT1; ++nt) {
+          float* y = dE + (size_t)(row0 + mt * 16 + g8) * 36 + nt * 8 + 2 * t4;
+          *reinterpret_cast<float2*>(y) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+          *reinterpret_cast<float2*>(y + 8 * 36) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+        }
+    }
+    __syncwarp();
+    // ============ 7. grid-gradient scatter + pose Jacobian (path A: positions) for this thread's point
+    {
+      const float* dE = reinterpret_cast<const float*>(X3) + (size_t)tid * 36;
+      float gx[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+#pragma unroll 2
+        for (int l = 0; l < L; ++l) {
+          const float2 g = *reinterpret_cast<const float2*>(dE + 2 * l);
+          if (g.x != 0.f || g.y != 0.f) scatter_level(a.p.grad_table, lv, l, u, g.x, g.y);
+          if (a.p.need_pose_grad) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const float2 j = __half22float2(Jslot[(size_t)(l * 3 + d) * T + tid]);
+              gx[d] = fmaf(g.x, j.x, fmaf(g.y, j.y, gx[d]));
+            }
+          }
+        }
+      }
+      if (a.p.need_pose_grad) {
+        // dL/dx = 0.5 * dL/du ; dL/dR[i][j] += gx[i]*pc[j] ; dL/dt[i] += gx[i]   (x = R pc + t)
+        float gtf[12];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float gi = 0.5f * gx[i];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) gtf[i * 4 + j] = gi * pc[j];
+          gtf[i * 4 + 3] = gi;
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) gtf[i] = warp_sum(gtf[i]);
+        if (lane == 0 && rs.active && rs.frame != 0) {
+#pragma unroll
+          for (int i = 0; i < 12; ++i)
+            if (gtf[i] != 0.f) red_add(a.p.grad_tf + (size_t)rs.frame * 12 + i, gtf[i]);
+        }
+      }
+    }
+    __syncthreads();                                        // dviews complete; rays/buffers free for the next tile
+    // ---- path B: view directions (per ray): dviews -> dfeat, dSH -> d(dir_w) -> dR
+    if (tid < R && sRay[tid].active) {
+      RayS& r2 = sRay[tid];
+      if (a.p.grad_feat) {
+        for (int j = 0; j < a.p.ff; ++j)
+          if (r2.dviews[j] != 0.f) red_add(a.p.grad_feat + (size_t)r2.frame * a.p.ff + j, r2.dviews[j]);
+      }
+      if (a.p.need_pose_grad && r2.frame != 0) {
+        float gd[3];
+        sh3_backward(r2.dw, r2.dviews + a.p.ff, gd);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float v = gd[i] * r2.u[j];
+            if (v != 0.f) red_add(a.p.grad_tf + (size_t)r2.frame * 12 + i * 4 + j, v);
+          }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ============ flush: weight gradients (registers -> global, fp32 atomics), losses, flags
+  {
+    float* G = a.p.grad_mlp;
+    const int K3 = V + 15;
+#pragma unroll
+    for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
+      const int uid = s * NW + warp;
+      if (uid >= um.total) continue;
+      int strip, nt0, ncols, nrows, wofs, bofs;
+      if (uid < um.l2) { constexpr int G1 = (KE / 8 + 3) / 4; const int k = uid - um.l1; strip = k / G1; nt0 = (k % G1) * 4; ncols = E; nrows = 64; wofs = a.po[0]; bofs = a.po[1]; }
+      else if (uid < um.l3) { strip = 0; nt0 = (uid - um.l2) * 4; ncols = 64; nrows = 16; wofs = a.po[2]; bofs = a.po[3]; }
+      else if (uid < um.l4) { strip = uid - um.l3; nt0 = 0; ncols = K3; nrows = 64; wofs = a.po[4]; bofs = a.po[5]; }
+      else if (uid < um.l5) { const int k = uid - um.l4; strip = k >> 1; nt0 = (k & 1) * 4; ncols = 64; nrows = 64; wofs = a.po[6]; bofs = a.po[7]; }
+      else { strip = 0; nt0 = (uid - um.l5) * 4; ncols = 64; nrows = 3; wofs = a.po[8]; bofs = a.po[9]; }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int o = strip * 16 + g8 + h * 8, i = (nt0 + nt) * 8 + 2 * t4 + c;
+            const float v = wg.w[s][nt][h * 2 + c];
+            if (o < nrows && i < ncols && v != 0.f) red_add(G + wofs + (size_t)o * ncols + i, v);
+          }
+      if (nt0 == 0 && t4 == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int o = strip * 16 + g8 + h * 8;
+          if (o < nrows && wg.b[s][h] != 0.f) red_add(G + bofs + o, wg.b[s][h]);
+        }
+      }
+    }
+  }
+  {
+    loss_acc[0] = loss_acc[1] + loss_acc[2] + loss_acc[3] + loss_acc[4];
+    float vals[7] = {loss_acc[0], loss_acc[1], loss_acc[2], loss_acc[3], loss_acc[4], n_valid_s, n_valid_r};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const float v = warp_sum(vals[i]);
+      if (lane == 0 && v != 0.f) red_add(a.p.losses + i, v);
+    }
+    const unsigned ov = __ballot_sync(0xffffffffu, overflow);
+    if (lane == 0 && ov && a.p.found_inf) atomicExch(a.p.found_inf, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t step_amp_smem(int T, int KE) { return (size_t)make_plan(T, KE).total; }
+
+template <int NW, int KE>
+static int launch_amp(const StepArgs& a, int blocks, cudaStream_t st) {
+  const size_t smem = step_amp_smem(NW * 32, KE);
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(step_amp_kernel<NW, KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    once = true;
+  }
+  step_amp_kernel<NW, KE><<<blocks, NW * 32, smem, st>>>(a);
+  return check_launch("step_amp_kernel");
+}
+
+int step_amp_dispatch(const StepArgs& a, int NW, int blocks, cudaStream_t st) {
+#define NOF_AMP_CASE(nw)                                                     \
+  case nw:                                                                   \
+    if (a.KE == 32) return launch_amp<nw, 32>(a, blocks, st);                \
+    if (a.KE == 16) return launch_amp<nw, 16>(a, blocks, st);                \
+    break;
+  switch (NW) {
+    NOF_AMP_CASE(4)
+    NOF_AMP_CASE(6)
+    NOF_AMP_CASE(8)
+    NOF_AMP_CASE(10)
+    default: break;
+  }
+#undef NOF_AMP_CASE
+  set_error("nof_step_fused(amp): unsupported tile NW=%d KE=%d", NW, a.KE);
+  return NOF_E_UNSUPPORTED;
+}
+
+}  // namespace nof

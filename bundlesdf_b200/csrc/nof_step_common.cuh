@@ -1,0 +1,280 @@
+// Shared device code of the fused train-step kernels (fp16 tensor-core policy in nof_step_amp.cu, fp32 policy in
+// nof_step_f32.cu): per-ray setup, point generation, hash-grid gather with d enc/d x, compositing weights,
+// loss seeds (dL/draw), grid-gradient scatter and the pose Jacobian reductions.
+//
+// Thread mapping: a CTA owns R whole rays; thread = one sample point (Sp = S rounded up to 32 lanes per ray, so a
+// warp never straddles two rays). Because a CTA sees complete rays, forward, loss and backward run back to back in
+// one kernel and no per-point intermediate ever leaves the SM except the d enc/d x block J, which goes to a per-CTA
+// scratch slot that is reused every tile and therefore lives in L2.
+#pragma once
+#include "nof_common.cuh"
+
+namespace nof {
+
+constexpr int KC = 32;          // padded width of the colour-net input [views(ff+9) | geo(15) | 0...]
+constexpr int MAX_L = 16;
+constexpr int MAX_R = 4;        // rays per CTA
+constexpr int MAX_V = 17;       // ff <= 8
+
+struct StepArgs {
+  NofStep p;
+  int E, V, KE;                 // enc width L*C, view width ff+9, enc width padded to 16
+  int po[10];                   // element offsets of W1 b1 W2 b2 W3 b3 W4 b4 W5 b5 in the packed block
+  int R, Sp, n_groups;          // rays per CTA, lanes per ray, number of ray groups
+  float inv_N3, inv_NS, inv_NS3;
+};
+
+struct RayS {                   // per-ray shared state
+  float dir[3], u[3];           // camera-frame dir (non-unit) and its unit vector
+  float dw[3];                  // world-frame unit view dir R*u
+  float gt[3];
+  float depth, ray_w_base;      // first_frame_weight or 1, times (type==0)
+  float tf[12];
+  int frame, ray, active;
+  float sumw;                   // sum of raw compositing weights over the ray's samples
+  float rgb[3];                 // composited colour
+  int anyvalid;
+  float views[MAX_V];           // [frame feature | SH(dw)] fp32
+  float dviews[KC];             // sum over samples of dL/d(colour-net input)[0..V)
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// SH degree 3 (nerf_helpers.py:72-85) and its Jacobian contraction: g_dir += J^T g_sh
+__device__ __forceinline__ void sh3(const float d[3], float* out) {
+  const float x = d[0], y = d[1], z = d[2];
+  out[0] = 0.28209479177387814f;
+  out[1] = -0.4886025119029199f * y;
+  out[2] = 0.4886025119029199f * z;
+  out[3] = -0.4886025119029199f * x;
+  out[4] = 1.0925484305920792f * (x * y);
+  out[5] = -1.0925484305920792f * (y * z);
+  out[6] = 0.31539156525252005f * (2.0f * (z * z) - x * x - y * y);
+  out[7] = -1.0925484305920792f * (x * z);
+  out[8] = 0.5462742152960396f * (x * x - y * y);
+}
+__device__ __forceinline__ void sh3_backward(const float d[3], const float* g, float gd[3]) {
+  const float x = d[0], y = d[1], z = d[2];
+  const float C1 = 0.4886025119029199f, A = 1.0925484305920792f, Bc = 0.31539156525252005f, Cc = 0.5462742152960396f;
+  gd[0] = -C1 * g[3] + A * y * g[4] - 2.f * Bc * x * g[6] - A * z * g[7] + 2.f * Cc * x * g[8];
+  gd[1] = -C1 * g[1] + A * x * g[4] - A * z * g[5] - 2.f * Bc * y * g[6] - 2.f * Cc * y * g[8];
+  gd[2] = C1 * g[2] - A * y * g[5] + 4.f * Bc * z * g[6] - A * x * g[7];
+}
+
+// Per-level constants staged in shared memory once per CTA.
+struct LevelS {
+  float scale[MAX_L];
+  uint32_t res1[MAX_L];         // resolution + 1
+  uint32_t hsize[MAX_L];
+  uint32_t off[MAX_L];
+  uint32_t dense[MAX_L];
+};
+
+__device__ __forceinline__ void init_levels(LevelS& lv, const StepArgs& a) {
+  if (threadIdx.x < a.p.L) {
+    LevelGeom g = level_geom3(threadIdx.x, a.p.S_log2, a.p.H, a.p.offsets);
+    lv.scale[threadIdx.x] = g.scale;
+    lv.res1[threadIdx.x] = g.resolution + 1u;
+    lv.hsize[threadIdx.x] = g.hashmap_size;
+    lv.off[threadIdx.x] = g.offset;
+    lv.dense[threadIdx.x] = g.dense;
+  }
+}
+
+__device__ __forceinline__ uint32_t corner_idx(uint32_t dense, uint32_t r1, uint32_t hsize, uint32_t x, uint32_t y, uint32_t z) {
+  if (dense) return x + y * r1 + z * r1 * r1;                    // < hsize by construction (gridencoder.cu:70-73)
+  return ((x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u)) % hsize;  // gridencoder.cu:78-82
+}
+
+template <bool HALF> struct TableT;
+template <> struct TableT<true> {
+  using vec = __half2;
+  static __device__ __forceinline__ float2 load(const void* table, uint32_t entry) {
+    const __half2 h = __ldg(reinterpret_cast<const __half2*>(table) + entry);
+    return __half22float2(h);
+  }
+};
+template <> struct TableT<false> {
+  using vec = float2;
+  static __device__ __forceinline__ float2 load(const void* table, uint32_t entry) {
+    return __ldg(reinterpret_cast<const float2*>(table) + entry);
+  }
+};
+
+// Setup of the R rays of one group (threads 0..R-1), nerf_runner.py:1045-1057,1282-1283.
+__device__ __forceinline__ void setup_ray(RayS& rs, const StepArgs& a, int ray) {
+  rs.ray = ray;
+  rs.active = ray < a.p.N;
+  rs.sumw = 0.f; rs.rgb[0] = rs.rgb[1] = rs.rgb[2] = 0.f; rs.anyvalid = 0;
+#pragma unroll
+  for (int i = 0; i < KC; ++i) rs.dviews[i] = 0.f;
+  if (!rs.active) {
+    rs.frame = 0; rs.depth = 0.f; rs.ray_w_base = 0.f;
+    for (int i = 0; i < 3; ++i) { rs.dir[i] = 0.f; rs.u[i] = 0.f; rs.dw[i] = 0.f; rs.gt[i] = 0.f; }
+    for (int i = 0; i < 12; ++i) rs.tf[i] = 0.f;
+    for (int i = 0; i < MAX_V; ++i) rs.views[i] = 0.f;
+    return;
+  }
+  const float* row = a.p.rays + (size_t)ray * a.p.ray_dim;
+  const float dx = row[0], dy = row[1], dz = row[2];
+  rs.dir[0] = dx; rs.dir[1] = dy; rs.dir[2] = dz;
+  const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+  rs.u[0] = dx / nrm; rs.u[1] = dy / nrm; rs.u[2] = dz / nrm;
+  rs.gt[0] = row[3]; rs.gt[1] = row[4]; rs.gt[2] = row[5];
+  rs.depth = row[6];
+  rs.frame = min(max((int)row[8], 0), a.p.F - 1);
+  const float type = row[9];
+  rs.ray_w_base = (type == 0.f) ? ((rs.frame == 0) ? a.p.first_frame_weight : 1.0f) : 0.f;   // nerf_runner.py:693-698,723
+  const float* T = a.p.tf + (size_t)rs.frame * 12;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) rs.tf[i] = T[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) rs.dw[i] = T[i * 4 + 0] * rs.u[0] + T[i * 4 + 1] * rs.u[1] + T[i * 4 + 2] * rs.u[2];
+  for (int j = 0; j < a.p.ff; ++j) rs.views[j] = a.p.feat[(size_t)rs.frame * a.p.ff + j];
+  sh3(rs.dw, rs.views + a.p.ff);
+}
+
+// Raw (un-normalised) compositing weight, nerf_runner.py:1152-1159.
+__device__ __forceinline__ float raw_weight(const StepArgs& a, float z, float depth) {
+  if (depth > a.p.far_sc) return 0.f;
+  const float s = (depth - z) / a.p.trunc;
+  float w = sigmoidf_(s * a.p.sdf_lambda) * sigmoidf_(-s * a.p.sdf_lambda);
+  const float dz = z - depth;
+  const bool m = (dz <= a.p.trunc * a.p.neg_trunc_ratio) && (dz >= -a.p.trunc);
+  return m ? w : 0.f;
+}
+
+// World point of this thread's sample: x = R (dir*z) + t (nerf_runner.py:1083,1242-1243).
+__device__ __forceinline__ void world_point(const RayS& rs, float z, float pc[3], float x[3]) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) pc[j] = rs.dir[j] * z;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    x[i] = fmaf(rs.tf[i * 4 + 2], pc[2], fmaf(rs.tf[i * 4 + 1], pc[1], rs.tf[i * 4 + 0] * pc[0])) + rs.tf[i * 4 + 3];
+}
+
+// One level of the multires gather for one point: enc (C=2) and, if WANT_J, J[d][c] = d enc/d u (gridencoder.cu:155-245).
+template <bool HALF, bool WANT_J>
+__device__ __forceinline__ void gather_level(const void* table, const LevelS& lv, int l, const float u[3], float enc[2],
+                                             float J[3][2]) {
+  const float scale = lv.scale[l];
+  const uint32_t r1 = lv.res1[l], hs = lv.hsize[l], off = lv.off[l], dense = lv.dense[l];
+  float fr[3];
+  uint32_t pg[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float p = fmaf(u[d], scale, 0.5f);
+    const float fl = floorf(p);
+    pg[d] = (uint32_t)fl;
+    fr[d] = p - fl;
+  }
+  float2 f[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t idx = corner_idx(dense, r1, hs, pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1));
+    f[c] = TableT<HALF>::load(table, off + idx);
+  }
+  const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
+  float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float w = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
+    e0 = fmaf(w, f[c].x, e0);
+    e1 = fmaf(w, f[c].y, e1);
+  }
+  enc[0] = e0; enc[1] = e1;
+  if (WANT_J) {
+#pragma unroll
+    for (int gd = 0; gd < 3; ++gd) {
+      float j0 = 0.f, j1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // the two other dims
+        const int d0 = (gd == 0) ? 1 : 0, d1 = (gd == 2) ? 1 : 2;
+        const int b0 = k & 1, b1 = (k >> 1) & 1;
+        const float w0 = (d0 == 0 ? wx[b0] : wy[b0]);
+        const float w1 = (d1 == 2 ? wz[b1] : wy[b1]);
+        const float w = scale * w0 * w1;
+        const int base = (b0 << d0) | (b1 << d1);
+        const float2 lo = f[base], hi = f[base | (1 << gd)];
+        j0 = fmaf(w, hi.x - lo.x, j0);
+        j1 = fmaf(w, hi.y - lo.y, j1);
+      }
+      J[gd][0] = j0; J[gd][1] = j1;
+    }
+  }
+}
+
+// Scatter dL/d enc of one level into the fp32 gradient table (gridencoder.cu:250-336, fp32 accumulate instead of
+// fp16 atomics) — one vectorised reduction per corner.
+__device__ __forceinline__ void scatter_level(float* grad_table, const LevelS& lv, int l, const float u[3], float g0, float g1) {
+  const float scale = lv.scale[l];
+  const uint32_t r1 = lv.res1[l], hs = lv.hsize[l], off = lv.off[l], dense = lv.dense[l];
+  float fr[3];
+  uint32_t pg[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float p = fmaf(u[d], scale, 0.5f);
+    const float fl = floorf(p);
+    pg[d] = (uint32_t)fl;
+    fr[d] = p - fl;
+  }
+  const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t idx = corner_idx(dense, r1, hs, pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1));
+    const float w = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
+    red_add_v2(grad_table + ((size_t)(off + idx)) * 2, w * g0, w * g1);
+  }
+}
+
+// Loss seeds for one sample (nerf_runner.py:693-732, nerf_helpers.py:367-399). Inputs: network output (rgb logits,
+// sdf), normalised compositing weight w (already 0 for invalid samples), ray weight. Returns dL/draw (unscaled) and
+// accumulates the per-term loss values into acc[5] = {total, rgb(unused here), fs, sdf, fs_rgb}.
+__device__ __forceinline__ void loss_seeds(const StepArgs& a, const RayS& rs, const float out[4], float z, float w, bool valid,
+                                           float ray_w, float d_out[4], float acc[5]) {
+  const float sw = valid ? ray_w : 0.f;
+  const float depth = rs.depth;
+  float rgb_s[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    rgb_s[c] = sigmoidf_(out[c]);
+    const float dmap = a.p.rgb_weight * 2.f * (rs.rgb[c] - rs.gt[c]) * ray_w * a.inv_N3;
+    d_out[c] = dmap * w * rgb_s[c] * (1.f - rgb_s[c]);
+  }
+  const float sdf = out[3];
+  const float tr = a.p.trunc;
+  const bool front = z < depth - tr;
+  const bool back = z > depth + tr * a.p.neg_trunc_ratio;
+  const bool valid_depth = (depth >= a.p.near_sc) && (depth <= a.p.far_sc);
+  const bool m_sdf = !front && !back && valid_depth;
+  float ds = 0.f;
+  // uncertain free space (nerf_helpers.py:387-389)
+  if (depth > a.p.far_sc && sdf < a.p.fs_sdf) {
+    const float e = sdf - a.p.fs_sdf;
+    acc[2] += a.p.fs_weight * 0.5f * e * e * sw * a.inv_NS;
+    ds += a.p.fs_weight * e * sw * a.inv_NS;
+  }
+  // empty space in front of the surface (nerf_helpers.py:391-393)
+  if (front && depth <= a.p.far_sc && sdf < 1.f) {
+    acc[2] += a.p.fs_weight * a.p.empty_weight * fabsf(sdf - 1.f) * sw * a.inv_NS;
+    ds += -a.p.fs_weight * a.p.empty_weight * sw * a.inv_NS;
+  }
+  // truncated sdf near the surface (nerf_helpers.py:395)
+  if (m_sdf) {
+    const float e = (z + sdf * tr) - depth;
+    acc[3] += a.p.trunc_weight * 0.5f * e * e * sw * a.inv_NS;
+    ds += a.p.trunc_weight * e * tr * sw * a.inv_NS;
+  }
+  if (a.p.fs_rgb_weight > 0.f && front) {       // nerf_runner.py:730-732
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float e = rgb_s[c] - 1.f;
+      acc[4] += a.p.fs_rgb_weight * e * e * sw * a.inv_NS3;
+      d_out[c] += a.p.fs_rgb_weight * 2.f * e * sw * a.inv_NS3 * rgb_s[c] * (1.f - rgb_s[c]);
+    }
+  }
+  d_out[3] = ds;
+}
+
+}  // namespace nof

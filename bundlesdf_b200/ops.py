@@ -1,0 +1,130 @@
+"""Thin functional wrappers over the fused C-ABI entry points (include/nof.h §2). Tensors in, tensors out; all launches
+go to torch's current stream; nothing here synchronises with the host."""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NofAdamSeg, NofMarchCfg, NofStep
+
+
+def mlp_param_layout(E, V):
+    """(padded element count, offsets[10]) of the packed MLP block W1 b1 W2 b2 W3 b3 W4 b4 W5 b5."""
+    lib = _lib.load()
+    offs = (C.c_int32 * 10)()
+    _lib.check(lib.nof_mlp_param_offsets(E, V, offs), 'nof_mlp_param_offsets')
+    return int(lib.nof_mlp_param_count(E, V)), [int(o) for o in offs]
+
+
+MLP_KEYS = ['sigma_net.0.weight', 'sigma_net.0.bias', 'sigma_net.2.weight', 'sigma_net.2.bias', 'color_net.0.weight',
+            'color_net.0.bias', 'color_net.2.weight', 'color_net.2.bias', 'color_net.4.weight', 'color_net.4.bias']
+
+
+def mlp_shapes(E, V):
+    return [(64, E), (64,), (16, 64), (16,), (64, V + 15), (64,), (64, 64), (64,), (3, 64), (3,)]
+
+
+def pack_occupancy(occ):
+    """bool [n,n,n] (indexed [x,y,z]) -> int32 tensor of bit words, bit = (ix*n+iy)*n+iz (host side, numpy)."""
+    flat = np.asarray(occ, dtype=bool).reshape(-1)
+    pad = (-len(flat)) % 32
+    if pad:
+        flat = np.concatenate([flat, np.zeros(pad, bool)])
+    words = np.packbits(flat.reshape(-1, 32)[:, ::-1], axis=1).view('>u4').astype(np.uint32).reshape(-1)
+    return torch.from_numpy(words.view(np.int32).copy())
+
+
+def pose_forward(pose_data, c2w, max_trans, max_rot_deg, out=None):
+    lib = _lib.load()
+    F = c2w.shape[0]
+    tf = out if out is not None else torch.empty(F, 12, device=c2w.device, dtype=torch.float32)
+    _lib.check(lib.nof_pose_forward(_lib.ptr(pose_data), _lib.ptr(c2w), _lib.ptr(tf), F, float(max_trans), float(max_rot_deg),
+                                    _lib.stream()), 'nof_pose_forward')
+    return tf
+
+
+def pose_backward(pose_data, c2w, grad_tf, grad_pose, max_trans, max_rot_deg, loss_scale=None):
+    lib = _lib.load()
+    _lib.check(lib.nof_pose_backward(_lib.ptr(pose_data), _lib.ptr(c2w), _lib.ptr(grad_tf), _lib.ptr(grad_pose), c2w.shape[0],
+                                     float(max_trans), float(max_rot_deg), _lib.ptr(loss_scale), _lib.stream()), 'nof_pose_backward')
+    return grad_pose
+
+
+def gather_rays(pool, ids, out=None):
+    lib = _lib.load()
+    N, D = ids.shape[0], pool.shape[1]
+    batch = out if out is not None else torch.empty(N, D, device=pool.device, dtype=torch.float32)
+    _lib.check(lib.nof_gather_rays(_lib.ptr(pool), _lib.ptr(ids), _lib.ptr(batch), N, D, _lib.stream()), 'nof_gather_rays')
+    return batch
+
+
+def ray_march(rays, tf, occ_bits, level, S_occ, S_depth, trunc, near_sc, far_sc, neg_trunc_ratio, t_rand=None, perturb=True,
+              seed=0, offset=0, I_max=None, z_vals=None, want_intervals=False, err_flag=None):
+    lib = _lib.load()
+    N, D = rays.shape
+    if I_max is None:
+        I_max = 3 * (1 << level)
+    S = S_occ + S_depth
+    if z_vals is None:
+        z_vals = torch.empty(N, S, device=rays.device, dtype=torch.float32)
+    inter = torch.empty(N, I_max, 2, device=rays.device, dtype=torch.float32) if want_intervals else None
+    cfg = NofMarchCfg(N, D, S_occ, S_depth, level, I_max, float(trunc), float(near_sc), float(far_sc), float(neg_trunc_ratio),
+                      int(bool(perturb)), int(seed), int(offset))
+    _lib.check(lib.nof_ray_march(C.byref(cfg), _lib.ptr(rays), _lib.ptr(tf), _lib.ptr(occ_bits), _lib.ptr(t_rand), _lib.ptr(z_vals),
+                                 _lib.ptr(inter), _lib.ptr(err_flag), _lib.stream()), 'nof_ray_march')
+    return (z_vals, inter) if want_intervals else z_vals
+
+
+class StepBuffers:
+    """Owns the NofStep argument block and keeps every tensor it points to alive."""
+
+    def __init__(self):
+        self.s = NofStep()
+        self.keep = {}
+
+    def set(self, **tensors):
+        for k, t in tensors.items():
+            self.keep[k] = t
+            setattr(self.s, k, _lib.ptr(t))
+
+    def set_scalars(self, **kw):
+        for k, v in kw.items():
+            setattr(self.s, k, v)
+
+    def workspace_bytes(self):
+        return int(_lib.load().nof_step_workspace_bytes(C.byref(self.s)))
+
+    def launch(self):
+        _lib.check(_lib.load().nof_step_fused(C.byref(self.s), _lib.stream()), 'nof_step_fused')
+
+
+LOSS_CFG_KEYS = ['sdf_lambda', 'neg_trunc_ratio', 'rgb_weight', 'fs_weight', 'empty_weight', 'trunc_weight', 'fs_sdf',
+                 'fs_rgb_weight', 'first_frame_weight']
+
+
+def fill_step_cfg(sb, cfg, trunc):
+    sc = cfg['sc_factor']
+    sb.set_scalars(trunc=float(trunc), near_sc=float(cfg['near'] * sc), far_sc=float(cfg['far'] * sc))
+    sb.set_scalars(**{k: float(cfg.get(k, 0)) for k in LOSS_CFG_KEYS})
+
+
+def adam_step(segs, beta1, beta2, eps, step, scale_state=None, found_inf=None):
+    """segs: list of dict(param, grad, exp_avg, exp_avg_sq, shadow_f16|None, lr). step: device int32 tensor [1]."""
+    lib = _lib.load()
+    arr = (NofAdamSeg * len(segs))()
+    for i, s in enumerate(segs):
+        n = s['param'].numel()
+        arr[i] = NofAdamSeg(_lib.ptr(s['param']), _lib.ptr(s['grad']), _lib.ptr(s['exp_avg']), _lib.ptr(s['exp_avg_sq']),
+                            _lib.ptr(s.get('shadow_f16')), n, float(s['lr']))
+    _lib.check(lib.nof_adam_step(arr, len(segs), float(beta1), float(beta2), float(eps), _lib.ptr(step), _lib.ptr(scale_state),
+                                 _lib.ptr(found_inf), _lib.stream()), 'nof_adam_step')
+
+
+def query_sdf(sb, x, out=None):
+    lib = _lib.load()
+    P = x.shape[0]
+    sdf = out if out is not None else torch.empty(P, device=x.device, dtype=torch.float32)
+    _lib.check(lib.nof_query_sdf(C.byref(sb.s), _lib.ptr(x), _lib.ptr(sdf), P, _lib.stream()), 'nof_query_sdf')
+    return sdf

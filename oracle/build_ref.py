@@ -57,10 +57,23 @@ def build_common():
                  os.path.join(OUT, 'common'))
 
 
+def stage_py():
+    """The reference's Python that needs its CUDA extensions (GridEncoder under autocast, the occupied-voxel sampler)
+    can only run on the GPU box, where /root/reference does not exist: stage the four files it needs into the
+    git-ignored oracle/_ref/py/ (travels with gpurun, never tracked) for tests/golden/make_golden_gpu.py."""
+    import shutil
+    dst = os.path.join(OUT, 'py')
+    os.makedirs(os.path.join(dst, 'mycuda', 'torch_ngp_grid_encoder'), exist_ok=True)
+    for f in ('nerf_helpers.py', 'nerf_runner.py', 'Utils.py'):
+        shutil.copy('/root/reference/' + f, os.path.join(dst, f))
+    shutil.copy(f'{REF}/torch_ngp_grid_encoder/grid.py', os.path.join(dst, 'mycuda', 'torch_ngp_grid_encoder', 'grid.py'))
+
+
 if __name__ == '__main__':
     if not os.path.isdir(REF):
         print('reference not mounted; nothing to build'); sys.exit(0)
     which = sys.argv[1:] or ['common', 'gridencoder']
+    stage_py()
     for w in which:
         t = time.time()
         {'common': build_common, 'gridencoder': build_gridencoder}[w]()

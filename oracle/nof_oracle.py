@@ -353,7 +353,7 @@ def ray_trace_intervals(occ, rays_o, rays_d, i_max=None):
                 break
             if a > b:
                 continue
-            if abs(b - a) < f32(1e-4):
+            if float(abs(f32(b - a))) < 1e-4:          # float diff promoted to double vs the literal 1e-4 (common.cu:140)
                 continue
             packed.append((a, b))
         out.append(packed)
@@ -380,7 +380,7 @@ def postprocess_octree_ray_tracing(ray_index, depth_in_out, unique_ids, start_po
                 break
             if a > b:
                 continue
-            if abs(b - a) < 1e-4:
+            if float(abs(np.float32(b - a))) < 1e-4:
                 continue
             out[i_ray, k] = (a, b)
             k += 1
@@ -441,49 +441,91 @@ def interval_walk(z_in_out, z_sampled):
     return z_vals, err
 
 
-def sample_along_rays(depths_in_out, dirs_cam, depth, cfg, trunc, t_rand_occ, t_rand_depth):
-    """nerf_runner.py:979-1011 + 1063-1081 for a batch whose rays all take the same branch structure.
-    depths_in_out torch [N,I,2] (travel times), dirs_cam [N,3] (non-unit camera dirs), depth [N].
-    t_rand_* : [N,S_occ] / [N,S_depth] uniform randoms or None. Returns z_vals [N,S_occ+S_depth], err."""
-    N = dirs_cam.shape[0]
+def linspace01_cuda(S):
+    """torch.linspace(0,1,S) as evaluated by torch's CUDA kernel (what the reference actually runs,
+    nerf_runner.py:74): step=(end-start)/(steps-1); idx<steps/2: start+step*idx, else end-step*(steps-idx-1),
+    each contracted to a single FMA. (The CPU kernel, used by the golden fixture, differs in the last ulp.)"""
+    f32 = np.float32
+    if S == 1:
+        return np.zeros(1, f32)
+    step = f32(1.0) / f32(S - 1)
+    i = np.arange(S)
+    lo = (step * i.astype(f32)).astype(f32)
+    hi = (1.0 - np.float64(step) * (S - i - 1).astype(np.float64)).astype(f32)
+    return np.where(i < S // 2, lo, hi).astype(f32)
+
+
+def stratified_np(S, near, far, t_rand):
+    """sample_rays_uniform (nerf_runner.py:67-87) in numpy fp32, one rounding per operation, CUDA linspace."""
+    f32 = np.float32
+    t = linspace01_cuda(S)[None, :]
+    near = near.astype(f32).reshape(-1, 1)
+    far = far.astype(f32).reshape(-1, 1)
+    z = (near * (f32(1.0) - t)).astype(f32) + (far * t).astype(f32)
+    z = z.astype(f32)
+    if t_rand is not None:
+        mids = (f32(0.5) * (z[:, 1:] + z[:, :-1]).astype(f32)).astype(f32)
+        upper = np.concatenate([mids, z[:, -1:]], -1)
+        lower = np.concatenate([z[:, :1], mids], -1)
+        z = (lower + ((upper - lower).astype(f32) * t_rand.astype(f32)).astype(f32)).astype(f32)
+        z = np.minimum(np.maximum(z, near), far)
+    return z.astype(f32)
+
+
+def rays_world_np(batch, tf12):
+    """Unit camera dir, world origin, world unit dir per ray (nerf_runner.py:1045-1057) in the exact fp32 operation
+    order of the CUDA sampler: nrm=sqrt((dx*dx+dy*dy)+dz*dz); u=d/nrm; dw_i=(R_i0*u0+R_i1*u1)+R_i2*u2.
+    batch np [N,>=9], tf12 np [F,12]."""
+    f32 = np.float32
+    d = batch[:, 0:3].astype(f32)
+    nrm = np.sqrt(((d[:, 0] * d[:, 0]).astype(f32) + (d[:, 1] * d[:, 1]).astype(f32)).astype(f32) + (d[:, 2] * d[:, 2]).astype(f32)).astype(f32)
+    u = (d / nrm[:, None]).astype(f32)
+    T = tf12[batch[:, 8].astype(np.int64)].astype(f32).reshape(-1, 3, 4)
+    o = T[:, :, 3].copy()
+    dw = np.stack([(((T[:, a, 0] * u[:, 0]).astype(f32) + (T[:, a, 1] * u[:, 1]).astype(f32)).astype(f32)
+                    + (T[:, a, 2] * u[:, 2]).astype(f32)).astype(f32) for a in range(3)], -1)
+    return u, o, dw
+
+
+def sample_along_rays(depths_in_out, unit_dirs_cam, depth, cfg, trunc, t_rand):
+    """nerf_runner.py:979-1011 (occupied-voxel sampling) + :1063-1081 (around-depth samples) in numpy fp32 with the
+    operation order of the CUDA sampler. depths_in_out np [N,I,2] travel times; unit_dirs_cam np [N,3];
+    depth np [N]; t_rand np [N, S_occ+S_depth] or None (perturb off). Returns (z_vals np [N,S], err)."""
+    f32 = np.float32
+    N, I = depths_in_out.shape[:2]
     sc = cfg['sc_factor']
-    unit = dirs_cam / dirs_cam.norm(dim=-1, keepdim=True)
-    z_in_out = depths_in_out * torch.abs(unit[..., 2]).reshape(N, 1, 1)
-    d = depth.reshape(-1, 1)
-    near_sc, far_sc = cfg['near'] * sc, cfg['far'] * sc
-    valid_depth = ((d >= near_sc) & (d <= far_sc)).reshape(-1)
+    S_occ, S_d = cfg['N_samples'], cfg['N_samples_around_depth']
+    absz = np.abs(unit_dirs_cam[:, 2]).astype(f32)
+    z_io = (depths_in_out.astype(f32) * absz[:, None, None]).astype(f32)                 # :990
+    depth = depth.astype(f32)
+    near_sc, far_sc = f32(cfg['near'] * sc), f32(cfg['far'] * sc)
+    valid_depth = (depth >= near_sc) & (depth <= far_sc)
+    zmax = (depth + f32(trunc)).astype(f32)
+    clip_ok = valid_depth[:, None] & (z_io > 0).all(-1)                                   # :994-995
+    clipped = np.minimum(np.maximum(z_io, f32(0)), zmax[:, None, None])
+    z_clip = np.where(clip_ok[..., None], clipped, z_io).astype(f32)
 
-    def occupied(z_io, n_samples, t_rand, clip_depth):
-        z_io = z_io.clone()
-        if clip_depth is not None:
-            dd, vd = clip_depth
-            valid = vd.reshape(-1, 1) & (z_io > 0).all(dim=-1)                       # [N,I]
-            mx = (dd.reshape(-1, 1, 1) + trunc).expand_as(z_io)
-            clipped = torch.minimum(torch.clamp(z_io, min=0), mx)
-            z_io = torch.where(valid[..., None], clipped, z_io)
-        lens = z_io[:, :, 1] - z_io[:, :, 0]
-        total = lens.sum(dim=-1).reshape(-1, 1)
-        z_cont = sample_rays_uniform(n_samples, torch.zeros_like(total), total, t_rand)
-        z, err = interval_walk(z_io.numpy().astype(np.float32), z_cont.numpy().astype(np.float32))
-        return torch.from_numpy(z), err
+    def seq_total(io):
+        tot = np.zeros(N, f32)
+        for k in range(I):
+            tot = (tot + (io[:, k, 1] - io[:, k, 0]).astype(f32)).astype(f32)
+        return tot
 
-    z_occ, err = occupied(z_in_out, cfg['N_samples'], t_rand_occ, (d, valid_depth))
-    S_d = cfg['N_samples_around_depth']
+    tr_occ = None if t_rand is None else t_rand[:, :S_occ]
+    z_cont = stratified_np(S_occ, np.zeros(N, f32), seq_total(z_clip), tr_occ)
+    z_occ, err = interval_walk(z_clip, z_cont)
     if S_d > 0:
-        z_ad = torch.zeros(N, S_d)
-        if valid_depth.any():
-            nd = (d[valid_depth] - trunc).reshape(-1, 1)
-            fd = (d[valid_depth] + trunc * cfg['neg_trunc_ratio']).reshape(-1, 1)
-            tr = None if t_rand_depth is None else t_rand_depth[valid_depth]
-            z_ad[valid_depth] = sample_rays_uniform(S_d, nd, fd, tr)
-        inv = ~valid_depth
-        if inv.any():
-            tr = None if t_rand_depth is None else t_rand_depth[inv]
-            zi, e2 = occupied(z_in_out[inv], S_d, tr, None)
-            z_ad[inv] = zi
+        tr_d = None if t_rand is None else t_rand[:, S_occ:]
+        nd = (depth - f32(trunc)).astype(f32)
+        fd = (depth + (f32(trunc) * f32(cfg['neg_trunc_ratio'])).astype(f32)).astype(f32)
+        z_ad = stratified_np(S_d, nd, fd, tr_d)
+        if (~valid_depth).any():                                                          # :1074-1076
+            z_c2 = stratified_np(S_d, np.zeros(N, f32), seq_total(z_io), tr_d)
+            z_inv, e2 = interval_walk(z_io, z_c2)
+            z_ad = np.where(valid_depth[:, None], z_ad, z_inv)
             err = err or e2
-        z_occ = torch.cat((z_occ, z_ad), dim=-1)
-    return z_occ, err
+        z_occ = np.concatenate([z_occ, z_ad.astype(f32)], -1)
+    return z_occ.astype(f32), err
 
 
 # --------------------------------------------------------------------------------------------------
@@ -584,14 +626,19 @@ def forward_step(params, batch, c2w, occ, cfg, t_rand_occ=None, t_rand_depth=Non
     frame_ids = batch[:, 8].long()
     tf_all = frame_transforms(params, c2w, cfg)
     tf = tf_all[frame_ids]                                            # [N,4,4]
-    rays_o_w = tf[:, :3, 3]
     viewdirs_w = (tf[:, :3, :3] @ viewdirs[..., None])[..., 0]
     err = False
     if z_vals is None:
         with torch.no_grad():
-            io = ray_trace_intervals(occ, rays_o_w.detach().numpy().astype(np.float32),
-                                     viewdirs_w.detach().numpy().astype(np.float32))
-            z_vals, err = sample_along_rays(torch.from_numpy(io), rays_d, batch[:, 6], cfg, trunc, t_rand_occ, t_rand_depth)
+            tf12 = tf_all[:, :3, :].reshape(-1, 12).detach().float().numpy()
+            bnp = batch.detach().float().numpy()
+            u, o, dw = rays_world_np(bnp, tf12)
+            io = ray_trace_intervals(occ, o, dw)
+            t_rand = None
+            if t_rand_occ is not None:
+                t_rand = np.concatenate([np.asarray(t_rand_occ, np.float32)] + ([np.asarray(t_rand_depth, np.float32)] if t_rand_depth is not None else []), -1)
+            zv, err = sample_along_rays(io, u, bnp[:, 6], cfg, trunc, t_rand)
+            z_vals = torch.from_numpy(zv)
     z_vals = z_vals.to(rays_d.dtype)
     S = z_vals.shape[1]
     pts = rays_d[:, None, :] * z_vals[:, :, None]                      # nerf_runner.py:1083

@@ -1,0 +1,129 @@
+"""GPU parity of the fused path (pose -> ray march -> fused forward+loss+backward) against the CPU oracle with exact
+autograd gradients, at sizes the oracle finishes in seconds. Tolerances are stated per mode:
+  fp32 policy (cfg amp: false): forward <= 2e-5 rel, losses <= 1e-4 rel, gradients <= 2e-3 of the tensor's max |g|
+  AMP  policy (cfg amp: true) : compared with the oracle run with fp16 operand rounding; forward <= 3e-3,
+                                 losses <= 5e-3 rel, gradients <= 3e-2 of max |g|."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import nof_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(scene, t_rand, half):
+    cfg, P = scene['cfg'], scene['params']
+    P = dict(P)
+    leaves = ['embeddings'] + [k for k in P if 'net' in k]
+    if P.get('pose_data') is not None:
+        leaves.append('pose_data')
+    if P.get('feature_data') is not None:
+        leaves.append('feature_data')
+    for k in leaves:
+        P[k] = P[k].detach().clone().requires_grad_(True)
+    S_occ = cfg['N_samples']
+    out = O.forward_step(P, scene['batch'], scene['c2w'], scene['occ'], cfg, t_rand_occ=None if t_rand is None else t_rand[:, :S_occ],
+                         t_rand_depth=None if t_rand is None else t_rand[:, S_occ:], half=half)
+    out['loss'].backward()
+    return out, P
+
+
+def _rel_max(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.parametrize('L,finest,log2T,S_occ,S_d,N', [(4, 128, 14, 32, 32, 96), (16, 256, 12, 64, 64, 40), (16, 256, 12, 128, 64, 20)])
+def test_ray_march_matches_oracle(L, finest, log2T, S_occ, S_d, N):
+    scene = helpers.make_scene(n_frames=4, N=N, cfg=helpers.make_cfg(L, finest, log2T, S_occ, S_d), invalid_frac=0.1)
+    rng = np.random.default_rng(5)
+    t_rand = rng.random((N, S_occ + S_d), dtype=np.float32)
+    res = helpers.run_fused_step(scene, amp=False, t_rand=t_rand)
+    cfg, P = scene['cfg'], scene['params']
+    tf12 = res['tf'].cpu().numpy()
+    u, o, dw = O.rays_world_np(scene['batch'].numpy(), tf12)
+    io = O.ray_trace_intervals(scene['occ'], o, dw, i_max=3 * (1 << scene['level']))
+    np.testing.assert_array_equal(res['intervals'].cpu().numpy(), io)
+    zv, err = O.sample_along_rays(io, u, scene['batch'].numpy()[:, 6], cfg, O.get_truncation(cfg, 0), t_rand)
+    assert not err and res['march_err'] == 0
+    np.testing.assert_array_equal(res['z_vals'].cpu().numpy(), zv)
+    # no-perturb path
+    res2 = helpers.run_fused_step(scene, amp=False, t_rand=None)
+    zv2, _ = O.sample_along_rays(io, u, scene['batch'].numpy()[:, 6], cfg, O.get_truncation(cfg, 0), None)
+    np.testing.assert_array_equal(res2['z_vals'].cpu().numpy(), zv2)
+
+
+CASES = [
+    # L, finest, log2T, S_occ, S_d, N, ff, kwargs
+    (4, 128, 14, 32, 32, 64, 0, {}),                                   # C1-shaped (S=64, L=4)
+    (16, 256, 12, 64, 64, 48, 0, dict(invalid_frac=0.1, type1_frac=0.1)),   # C2/C3-shaped (S=128, L=16), invalid-depth + uncertain rays
+    (16, 256, 12, 128, 64, 18, 2, {}),                                 # reference default split 128+64, frame features on
+]
+
+
+@pytest.mark.parametrize('L,finest,log2T,S_occ,S_d,N,ff,kw', CASES)
+@pytest.mark.parametrize('amp', [False, True])
+def test_fused_step_matches_oracle(L, finest, log2T, S_occ, S_d, N, ff, kw, amp):
+    cfg = helpers.make_cfg(L, finest, log2T, S_occ, S_d, ff=ff)
+    if ff:
+        cfg['fs_rgb_weight'] = 0.5
+    scene = helpers.make_scene(n_frames=4, N=N, cfg=cfg, **kw)
+    rng = np.random.default_rng(11)
+    t_rand = rng.random((N, S_occ + S_d), dtype=np.float32)
+    ref, P = _oracle(scene, t_rand, half=amp)
+    res = helpers.run_fused_step(scene, amp=amp, t_rand=t_rand, loss_scale=(1024.0 if amp else None))
+    scale = 1024.0 if amp else 1.0
+    ftol, ltol, gtol = (3e-3, 5e-3, 3e-2) if amp else (2e-5, 1e-4, 2e-3)
+    np.testing.assert_array_equal(res['z_vals'].cpu().numpy(), ref['z_vals'].numpy())
+    np.testing.assert_array_equal(res['valid_samples'].cpu().numpy().astype(bool), ref['valid_samples'].numpy())
+    np.testing.assert_allclose(res['weights'].cpu().numpy(), ref['weights'].detach().numpy(), rtol=1e-4, atol=1e-7)
+    assert _rel_max(res['raw'].cpu().numpy(), ref['raw'].detach().numpy()) < ftol
+    np.testing.assert_allclose(res['rgb_map'].cpu().numpy(), ref['rgb_map'].detach().numpy(), rtol=ftol * 3, atol=ftol)
+    losses = res['losses'].cpu().numpy()
+    for i, k in [(0, 'loss'), (1, 'rgb_loss'), (2, 'fs_loss'), (3, 'sdf_loss')]:
+        want = float(ref[k].detach())
+        if k == 'loss':
+            want -= float(ref.get('reg_features', torch.tensor(0.0)).detach())      # host-side term (not in the kernel)
+        assert abs(losses[i] - want) <= ltol * max(abs(want), 1e-6), (k, losses[i], want)
+    assert losses[5] == float(ref['valid_samples'].sum())
+    # gradients
+    assert _rel_max(res['grad_table'].cpu().numpy() / scale, P['embeddings'].grad.numpy()) < gtol
+    for k, g in res['grad_mlp_named'].items():
+        assert _rel_max(g.cpu().numpy() / scale, P[k].grad.numpy()) < gtol, k
+    assert _rel_max(res['grad_pose'].cpu().numpy(), P['pose_data'].grad.numpy()) < gtol * 2
+    if ff:
+        want = P['feature_data'].grad.numpy() - (cfg['feature_reg_weight'] * 2 * scene['params']['feature_data'].numpy() / scene['params']['feature_data'].numel())
+        assert _rel_max(res['grad_feat'].cpu().numpy() / scale, want) < gtol
+    assert res['found_inf'].item() == 0
+
+
+def test_fused_step_no_pose_optimisation():
+    cfg = helpers.make_cfg(4, 128, 14, 32, 32, optimize_poses=0)
+    scene = helpers.make_scene(n_frames=3, N=32, cfg=cfg)
+    ref, P = _oracle(scene, None, half=False)
+    res = helpers.run_fused_step(scene, amp=False, t_rand=None)
+    assert _rel_max(res['grad_table'].cpu().numpy(), P['embeddings'].grad.numpy()) < 2e-3
+    assert torch.all(res['grad_tf'] == 0)
+
+
+def test_amp_overflow_sets_found_inf():
+    cfg = helpers.make_cfg(4, 128, 14, 32, 32)
+    scene = helpers.make_scene(n_frames=3, N=32, cfg=cfg)
+    res = helpers.run_fused_step(scene, amp=True, t_rand=None, loss_scale=1e12)
+    assert res['found_inf'].item() == 1
+
+
+def test_query_sdf_matches_oracle():
+    from bundlesdf_b200 import ops
+    cfg = helpers.make_cfg(16, 256, 12, 64, 64)
+    scene = helpers.make_scene(n_frames=3, N=16, cfg=cfg)
+    res = helpers.run_fused_step(scene, amp=False, t_rand=None)
+    P = scene['params']
+    x = (torch.rand(1000, 3) * 2.2 - 1.1)
+    xo = x.clamp(-1, 1)
+    enc = O.grid_encode((xo + 1) / 2, P['embeddings'], P['offsets'], P['S'], P['H'], exact_fma=False)
+    want = O.mlp_forward_sdf(P, enc)
+    got = ops.query_sdf(res['sb'], x.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
