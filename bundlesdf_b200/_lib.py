@@ -43,6 +43,7 @@ _SIGS = {
     'nof_device_info': (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'nof_grid_encode_forward': (C.c_int, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, C.c_int, _vp, _u32, C.c_int, C.c_int, _vp]),
     'nof_grid_encode_backward': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, C.c_int, _vp, _vp, _u32, C.c_int, C.c_int, _vp]),
+    'nof_grid_level_scales': (C.c_int, [_f32, _u32, C.c_int, _vp, _vp]),
     'nof_sample_rays_uniform_occupied_voxels': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     'nof_postprocess_octree_ray_tracing': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     'nof_gather_rays': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),

@@ -284,6 +284,11 @@ static int launch_bwd(const void* grad, const float* in, const int32_t* off, voi
   return rc;
 }
 
+__global__ void level_scales_kernel(float S, uint32_t H, int L, float* out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < L) out[l] = level_scale((uint32_t)l, S, H);
+}
+
 #define NOF_DISPATCH_DC(FN, ...)                                                              \
   do {                                                                                        \
     if (dtype == NOF_F32) {                                                                   \
@@ -335,4 +340,10 @@ extern "C" int nof_grid_encode_backward(const void* grad, const float* inputs, c
                   gridtype, align_corners != 0, st);
   set_error("nof_grid_encode_backward: D=%u C=%u dtype=%d not built", D, C, dtype);
   return NOF_E_UNSUPPORTED;
+}
+
+extern "C" int nof_grid_level_scales(float S, uint32_t H, int L, float* scales_out, nof_stream_t stream) {
+  NOF_REQUIRE(scales_out && L >= 1 && L <= 65535, "nof_grid_level_scales: bad arguments");
+  level_scales_kernel<<<div_up(L, 64), 64, 0, as_stream(stream)>>>(S, H, L, scales_out);
+  return check_launch("level_scales_kernel");
 }

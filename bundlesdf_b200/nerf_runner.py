@@ -1,0 +1,599 @@
+"""NerfRunner — the Neural-Object-Field trainer behind BundleSDF's API, B200-native.
+
+Same constructor / methods / attributes as the reference class (nerf_runner.py:111-1543 of NVlabs/BundleSDF) so that
+bundlesdf.py (run_nerf :64-260, run_global_nerf :636-767) can import this module unchanged:
+
+    NerfRunner(cfg, images, depths, masks, normal_maps, poses, K, _run=None, occ_masks=None, build_octree_pcd=None)
+    .add_new_frames(...)  .train()  .train_loop(batch)  .models[...]  .cfg  .extract_mesh(...)  .save_weights/.load_weights
+
+What differs is where the work happens. One train step of the reference is ~300-400 small PyTorch/cuBLAS/custom kernels
+with 3-5 host synchronisations; here it is six launches of hand-written sm_100a kernels on torch's current stream and no
+synchronisation:  gather rays -> pose correction -> ray march (occupancy DDA + stratified samples) -> ONE fused kernel
+(hash-grid gather, SDF+colour MLP on tensor cores, compositing, all losses, full backward incl. the pose Jacobian) ->
+pose backward -> fused Adam (+GradScaler semantics, fp16 shadow table, grad clear).  There is no CPU fallback: without
+the CUDA library the constructor raises.
+"""
+import copy
+import logging
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .nerf_helpers import BAD_DEPTH, FeatureArray, NeRFSmall, PoseArray, get_camera_rays_np, get_embedder
+from .occupancy import OctreeManager, build_occupancy_points
+
+
+def set_seed(random_seed):
+    """Utils.py:71-78."""
+    import random
+    np.random.seed(random_seed)
+    random.seed(random_seed)
+    torch.manual_seed(random_seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(random_seed)
+
+
+class DataLoader:
+    """Reference nerf_runner.py:90-107: epoch permutation from the CPU RNG, last partial batch dropped, reshuffle when
+    exhausted. The permutation is uploaded once per epoch; a step reads a slice of it on the device (no per-step H2D)."""
+
+    def __init__(self, rays, batch_size):
+        self.rays = rays
+        self.batch_size = batch_size
+        self.pos = 0
+        self._shuffle()
+
+    def _shuffle(self):
+        self.ids = torch.randperm(len(self.rays))
+        self.ids_dev = self.ids.to(self.rays.device)
+
+    def next_ids(self):
+        if self.pos + self.batch_size < len(self.ids):
+            sl = slice(self.pos, self.pos + self.batch_size)
+            self.pos += self.batch_size
+        else:
+            self._shuffle()
+            self.pos = self.batch_size
+            sl = slice(0, self.batch_size)
+        self.batch_ray_ids = self.ids[sl]
+        return self.ids_dev[sl]
+
+    def __next__(self):
+        ids = self.next_ids()
+        return ops.gather_rays(self.rays, ids.contiguous())
+
+
+class GradScalerState:
+    """Device-resident torch.cuda.amp.GradScaler state (init 65536, x2 / 2000 clean steps, x0.5 on inf; nerf_runner.py:159)."""
+
+    def __init__(self, enabled, device):
+        self.enabled = bool(enabled)
+        self.state = torch.tensor([65536.0 if enabled else 1.0, 0.0], device=device)
+        self.found_inf = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def get_scale(self):
+        return float(self.state[0].item())
+
+    def state_dict(self):
+        return {'scale': self.get_scale(), '_growth_tracker': int(self.state[1].item())}
+
+
+class NerfRunner:
+    def __init__(self, cfg, images, depths, masks, normal_maps, poses, K, _run=None, occ_masks=None, build_octree_pcd=None):
+        _lib.require_cuda()
+        _lib.load()
+        set_seed(0)
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self.cfg = cfg
+        self.cfg['tv_loss_weight'] = eval(str(self.cfg.get('tv_loss_weight', 0)))
+        self._run = _run
+        self.images, self.depths, self.masks, self.poses = images, depths, masks, poses
+        self.normal_maps, self.occ_masks = normal_maps, occ_masks
+        self.K = K.copy()
+        self.mesh = None
+        self.train_pose = False
+        self.N_iters = self.cfg['n_step'] + 1
+        self.build_octree_pts = np.asarray(build_octree_pcd.points).copy()
+        if normal_maps is not None:
+            raise NotImplementedError('normal_maps: the reference never feeds them to the loss (normal_loss_weight: 0); not built')
+
+        down = cfg['down_scale_ratio']
+        self.down_scale = np.ones((2), dtype=np.float32)
+        if down != 1:                                              # nerf_runner.py:129-148 (strided, no interpolation)
+            H, W = images[0].shape[:2]
+            down = int(down)
+            self.images = images[:, ::down, ::down]
+            self.depths = depths[:, ::down, ::down]
+            self.masks = masks[:, ::down, ::down]
+            if occ_masks is not None:
+                self.occ_masks = occ_masks[:, ::down, ::down]
+            self.H, self.W = self.images.shape[1:3]
+            self.cfg['dilate_mask_size'] = int(self.cfg['dilate_mask_size'] // down)
+            self.K[0] *= float(self.W) / W
+            self.K[1] *= float(self.H) / H
+            self.down_scale = np.array([float(self.W) / W, float(self.H) / H])
+        self.H, self.W = self.images[0].shape[:2]
+
+        self.octree_m = None
+        if self.cfg['use_octree']:
+            self.build_octree()
+        else:
+            raise NotImplementedError('use_octree: 0 — the shipped configs always sample through the occupancy structure')
+        self.create_nerf()
+        self.create_optimizer()
+        self.amp_scaler = GradScalerState(self.cfg['amp'], self.device)
+        self.global_step = 0
+        self.c2w_array = torch.tensor(np.asarray(poses)).float().to(self.device).contiguous()
+        self.best_models = None
+        self.best_loss = np.inf
+
+        rays = torch.cat([self.make_frame_rays(i) for i in range(len(self.masks))], dim=0)
+        if self.cfg['denoise_depth_use_octree_cloud']:
+            rays = self._denoise_rays(rays)
+        self.rays = rays.contiguous()
+        logging.info(f'rays {tuple(self.rays.shape)}')
+        self.data_loader = DataLoader(rays=self.rays, batch_size=self.cfg['N_rand'])
+        self._step_buf = None
+
+    # ------------------------------------------------------------------ model / optimizer
+    def create_nerf(self, device=None):
+        """nerf_runner.py:204-242: same modules, same creation order (=> same CPU-RNG initial weights for a given seed)."""
+        device = device or self.device
+        cfg = self.cfg
+        if cfg['N_importance'] > 0:
+            raise NotImplementedError('N_importance>0: dead code in the reference (nerf_runner.py:1106 unpacks 3 values into 2)')
+        if not cfg['use_viewdirs']:
+            raise NotImplementedError('use_viewdirs: 0 is not built (config.yml ships 1)')
+        models = {}
+        embed_fn, input_ch = get_embedder(cfg['multires'], cfg, i=cfg['i_embed'], octree_m=self.octree_m)
+        models['embed_fn'] = embed_fn.to(device)
+        embeddirs_fn, input_ch_views = get_embedder(cfg['multires_views'], cfg, i=cfg['i_embed_views'], octree_m=self.octree_m)
+        models['embeddirs_fn'] = embeddirs_fn
+        model = NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64, input_ch=input_ch,
+                          input_ch_views=input_ch_views + cfg['frame_features']).to(device)
+        models['model'] = model
+        models['model_fine'] = None
+        n_frames = len(self.images)
+        models['feature_array'] = FeatureArray(n_frames, cfg['frame_features']).to(device) if cfg['frame_features'] > 0 else None
+        models['pose_array'] = PoseArray(n_frames, max_trans=cfg['max_trans'] * cfg['sc_factor'], max_rot=cfg['max_rot']).to(device) \
+            if cfg['optimize_poses'] else None
+        self.models = models
+        self._bind_flat_buffers()
+
+    def _bind_flat_buffers(self):
+        """Re-home the MLP parameters in ONE packed device block (layout of nof_mlp_param_offsets) so the fused kernels stage
+        them with a single TMA bulk copy; module parameters become views of it (state_dict keys unchanged)."""
+        enc, model = self.models['embed_fn'], self.models['model']
+        self.E = enc.out_dim
+        self.V = 9 + self.cfg['frame_features']
+        assert enc.level_dim == 2, 'feature_grid_dim must be 2'
+        count, offs = ops.mlp_param_layout(self.E, self.V)
+        flat = torch.zeros(count, device=self.device)
+        named = dict(model.named_parameters())
+        for key, o, shp in zip(ops.MLP_KEYS, offs, ops.mlp_shapes(self.E, self.V)):
+            p = named[key]
+            assert tuple(p.shape) == tuple(shp), (key, p.shape, shp)
+            n = p.numel()
+            flat[o:o + n] = p.data.reshape(-1)
+            p.data = flat[o:o + n].view(shp)
+        self.mlp_flat, self.mlp_offs = flat, offs
+        self.table = enc.embeddings.data            # fp32 master [sO,2]
+        self.table_f16 = self.table.half() if self.cfg['amp'] else None
+        self.offsets_dev = enc.offsets.to(self.device).contiguous()
+
+    def create_optimizer(self):
+        """nerf_runner.py:492-504: Adam(betas=(0.9,0.999), eps=1e-15), group 'basic' (grid + MLP + features) at lrate and group
+        'pose_array' at lrate_pose. A torch.optim.Adam object carries param_groups / state_dict for checkpoints and the lr
+        schedule; the update itself is nof_adam_step over flat buffers that the optimizer state aliases."""
+        params = []
+        for k in self.models:
+            if self.models[k] is not None and k != 'pose_array':
+                params += list(self.models[k].parameters())
+        groups = [{'name': 'basic', 'params': params, 'lr': self.cfg['lrate']}]
+        if self.models['pose_array'] is not None:
+            groups.append({'name': 'pose_array', 'params': list(self.models['pose_array'].parameters()), 'lr': self.cfg['lrate_pose']})
+        self.optimizer = torch.optim.Adam(groups, betas=(0.9, 0.999), weight_decay=0, eps=1e-15)
+        self.param_groups_init = copy.deepcopy(self.optimizer.param_groups)
+        dev = self.device
+        z = lambda t: torch.zeros_like(t)
+        self.adam_step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        segs = [dict(name='table', param=self.table.view(-1), grad=z(self.table).view(-1), exp_avg=z(self.table).view(-1),
+                     exp_avg_sq=z(self.table).view(-1), shadow_f16=(self.table_f16.view(-1) if self.table_f16 is not None else None), group=0),
+                dict(name='mlp', param=self.mlp_flat, grad=z(self.mlp_flat), exp_avg=z(self.mlp_flat), exp_avg_sq=z(self.mlp_flat), group=0)]
+        fa, pa = self.models['feature_array'], self.models['pose_array']
+        if fa is not None:
+            segs.append(dict(name='feat', param=fa.data.data.view(-1), grad=z(fa.data.data).view(-1), exp_avg=z(fa.data.data).view(-1),
+                             exp_avg_sq=z(fa.data.data).view(-1), group=0))
+        if pa is not None:
+            segs.append(dict(name='pose', param=pa.data.data.view(-1), grad=z(pa.data.data).view(-1), exp_avg=z(pa.data.data).view(-1),
+                             exp_avg_sq=z(pa.data.data).view(-1), group=1))
+        self.adam_segs = {s['name']: s for s in segs}
+        # expose .grad and optimizer.state as views of the flat buffers (checkpoint / inspection parity)
+        enc, model = self.models['embed_fn'], self.models['model']
+        enc.embeddings.grad = self.adam_segs['table']['grad'].view_as(self.table)
+        st = self.optimizer.state
+        st[enc.embeddings] = {'step': self.adam_step_count, 'exp_avg': self.adam_segs['table']['exp_avg'].view_as(self.table),
+                              'exp_avg_sq': self.adam_segs['table']['exp_avg_sq'].view_as(self.table)}
+        named = dict(model.named_parameters())
+        for key, o, shp in zip(ops.MLP_KEYS, self.mlp_offs, ops.mlp_shapes(self.E, self.V)):
+            n = int(np.prod(shp))
+            m = self.adam_segs['mlp']
+            named[key].grad = m['grad'][o:o + n].view(shp)
+            st[named[key]] = {'step': self.adam_step_count, 'exp_avg': m['exp_avg'][o:o + n].view(shp), 'exp_avg_sq': m['exp_avg_sq'][o:o + n].view(shp)}
+        for nm, mod in (('feat', fa), ('pose', pa)):
+            if mod is not None:
+                s = self.adam_segs[nm]
+                mod.data.grad = s['grad'].view_as(mod.data)
+                st[mod.data] = {'step': self.adam_step_count, 'exp_avg': s['exp_avg'].view_as(mod.data), 'exp_avg_sq': s['exp_avg_sq'].view_as(mod.data)}
+        self._step_buf = None
+
+    def schedule_lr(self):
+        """nerf_runner.py:579-583."""
+        for i, g in enumerate(self.optimizer.param_groups):
+            g['lr'] = self.param_groups_init[i]['lr'] * (self.cfg['decay_rate'] ** (float(self.global_step) / self.N_iters))
+
+    def get_truncation(self):
+        """nerf_runner.py:663-676."""
+        cfg = self.cfg
+        if cfg['trunc_decay_type'] == 'linear':
+            t = cfg['trunc_start'] - (cfg['trunc_start'] - cfg['trunc']) * float(self.global_step) / cfg['n_step']
+        elif cfg['trunc_decay_type'] == 'exp':
+            lamb = np.log(cfg['trunc'] / cfg['trunc_start']) / (cfg['n_step'] / 4)
+            t = max(cfg['trunc_start'] * np.exp(self.global_step * lamb), cfg['trunc'])
+        else:
+            t = cfg['trunc']
+        return t * cfg['sc_factor']
+
+    # ------------------------------------------------------------------ occupancy / ray pool (upstream of the hot path)
+    def build_octree(self):
+        """nerf_runner.py:436-489 with the dense occupancy stand-in for kaolin's SPC (see occupancy.py)."""
+        pts = torch.tensor(self.build_octree_pts).to(self.device).float()
+        centers, max_level, level = build_occupancy_points(pts, self.cfg)
+        assert centers.min() >= -1 and centers.max() <= 1
+        self.octree_m = OctreeManager(centers, max_level, level=level, device=self.device)
+
+    def make_frame_rays(self, frame_id):
+        """nerf_runner.py:246-316 on the device: [R,12] rows dir(3) rgb(3) depth mask frame type near far for the pixels of one
+        frame that survive mask dilation, depth validity, the [-1,1]^3 box test and the occupancy trace."""
+        cfg, dev = self.cfg, self.device
+        sc = cfg['sc_factor']
+        H, W = self.H, self.W
+        mask = torch.as_tensor(np.ascontiguousarray(self.masks[frame_id, ..., 0])).to(dev)
+        depth = torch.as_tensor(np.ascontiguousarray(self.depths[frame_id, ..., 0])).float().to(dev)
+        rgb = torch.as_tensor(np.ascontiguousarray(self.images[frame_id])).float().to(dev)
+        dirs = torch.as_tensor(get_camera_rays_np(H, W, self.K)).float().to(dev)
+        invalid_depth = ((depth < cfg['near'] * sc) | (depth > cfg['far'] * sc)) & (mask > 0)
+        self.ray_dir_slice, self.ray_rgb_slice, self.ray_depth_slice, self.ray_mask_slice = [0, 1, 2], [3, 4, 5], 6, 7
+        self.ray_frame_id_slice, self.ray_type_slice, self.ray_near_slice, self.ray_far_slice = 8, 9, 10, 11
+        # cv2.dilate with a k x k ones kernel (anchor k//2): window [x-k//2, x+k-1-k//2]
+        down = int(cfg['down_scale_ratio'])
+        k = 100 if frame_id == 0 else 60 // down
+        m = (mask > 0).float()[None, None]
+        a = k // 2
+        m = torch.nn.functional.pad(m, (a, k - 1 - a, a, k - 1 - a))
+        m = torch.nn.functional.max_pool2d(m, kernel_size=k, stride=1)[0, 0] > 0
+        if self.occ_masks is not None:
+            m &= ~(torch.as_tensor(np.ascontiguousarray(self.occ_masks[frame_id])).to(dev).reshape(H, W) > 0)
+        if cfg['rays_valid_depth_only']:
+            m &= ~invalid_depth
+        vs, us = torch.nonzero(m, as_tuple=True)
+        n = len(vs)
+        rows = torch.zeros(n, 12, device=dev)
+        rows[:, 0:3] = dirs[vs, us]
+        rows[:, 3:6] = rgb[vs, us]
+        rows[:, 6] = depth[vs, us]
+        rows[:, 7] = (mask[vs, us] > 0).float()
+        rows[:, 8] = float(frame_id)
+        rows[:, 9] = invalid_depth[vs, us].float()
+        rows = rows[rows[:, 9] == 0]
+        # compute_near_far_and_filter_rays (nerf_runner.py:39-65): slab test against bounding_box, keep tmin >= 0
+        pose = torch.as_tensor(np.asarray(self.poses[frame_id])).float().to(dev)
+        d_unit = rows[:, 0:3] / rows[:, 0:3].norm(dim=-1, keepdim=True)
+        d_w = (pose[:3, :3] @ rows[:, 0:3].T).T
+        d_w = d_w / (d_w.norm(dim=-1, keepdim=True) + 1e-10)
+        o_w = pose[:3, 3][None].expand_as(d_w)
+        bounds = torch.tensor(cfg['bounding_box'], device=dev).float().reshape(2, 3)
+        inv = 1.0 / d_w
+        t_lo = (bounds[0] - o_w) * inv
+        t_hi = (bounds[1] - o_w) * inv
+        tmin = torch.minimum(t_lo, t_hi).clamp(min=0).max(dim=-1)[0]
+        tmax = torch.maximum(t_lo, t_hi).min(dim=-1)[0]
+        hit = tmin <= tmax
+        rows = rows[hit]
+        rows[:, 10] = (d_unit[hit, 2] * tmin[hit]).abs()
+        rows[:, 11] = (d_unit[hit, 2] * tmax[hit]).abs()
+        # keep rays that enter an occupied cell (nerf_runner.py:302-314)
+        if len(rows):
+            tf = pose[:3, :].reshape(1, 12).contiguous()
+            probe = rows.clone()
+            probe[:, 8] = 0
+            _, inter = ops.ray_march(probe.contiguous(), tf, self.octree_m.occ_bits, self.octree_m.level, 1, 0, 0.0, 1.0, 0.0, 1.0,
+                                     t_rand=None, perturb=False, want_intervals=True)
+            rows = rows[inter[:, 0, 0] > 0]
+        return rows
+
+    def _denoise_rays(self, rays):
+        """nerf_runner.py:178-195: drop rays whose back-projected point is farther than 2 cm from the octree cloud (exact NN
+        distance, brute force on the device instead of a CPU cKDTree)."""
+        cfg, dev = self.cfg, self.device
+        sc = cfg['sc_factor']
+        mask = (rays[:, 7] > 0) & (rays[:, 6] <= cfg['far'] * sc)
+        idx = torch.nonzero(mask).reshape(-1)
+        pts = rays[idx, 0:3] * rays[idx, 6:7]
+        poses = torch.as_tensor(np.asarray(self.poses)).float().to(dev)
+        T = poses[rays[idx, 8].long()]
+        pts_w = (T[:, :3, :3] @ pts[..., None])[..., 0] + T[:, :3, 3]
+        cloud = torch.as_tensor(self.build_octree_pts).float().to(dev)
+        bad = torch.zeros(len(idx), dtype=torch.bool, device=dev)
+        for s in range(0, len(idx), 16384):
+            d = torch.cdist(pts_w[s:s + 16384], cloud).min(dim=1)[0]
+            bad[s:s + 16384] = d > 0.02 * sc
+        rays[idx[bad], 6] = BAD_DEPTH * sc
+        rays[idx[bad], 9] = 1
+        logging.info(f'bad_mask#={int(bad.sum())}')
+        return rays[rays[:, 9] == 0]
+
+    def add_new_frames(self, images, depths, masks, normal_maps, poses, occ_masks=None, new_pcd=None, reuse_weights=False):
+        """nerf_runner.py:352-433."""
+        prev_n = len(self.images)
+        down = int(self.cfg['down_scale_ratio'])
+        images, depths, masks = images[:, ::down, ::down], depths[:, ::down, ::down], masks[:, ::down, ::down]
+        if occ_masks is not None:
+            self.occ_masks = np.concatenate((self.occ_masks, occ_masks[:, ::down, ::down]), axis=0)
+        self.images = np.concatenate((self.images, images), axis=0)
+        self.depths = np.concatenate((self.depths, depths), axis=0)
+        self.masks = np.concatenate((self.masks, masks), axis=0)
+        self.poses = poses.copy()
+        self.c2w_array = torch.tensor(np.asarray(poses), dtype=torch.float).to(self.device).contiguous()
+        if self.cfg['use_octree']:
+            pcd = new_pcd.voxel_down_sample(0.005)
+            self.build_octree_pts = np.asarray(pcd.points).copy()
+            self.build_octree()
+        if not reuse_weights:
+            self.create_nerf()
+        else:
+            n = len(self.images)
+            if self.cfg['frame_features'] > 0:
+                fa = FeatureArray(n, self.cfg['frame_features']).to(self.device)
+                fa.data.data[:prev_n] = self.models['feature_array'].data.data[:prev_n].detach().clone()
+                self.models['feature_array'] = fa
+            if self.cfg['optimize_poses']:
+                self.models['pose_array'] = PoseArray(n, max_trans=self.cfg['max_trans'] * self.cfg['sc_factor'], max_rot=self.cfg['max_rot']).to(self.device)
+        self.create_optimizer()
+        self.global_step = 0
+        self.best_models, self.best_loss = None, np.inf
+        if not self.cfg['no_batching']:
+            rays = torch.cat([self.make_frame_rays(i) for i in range(prev_n, len(self.masks))], dim=0)
+            if self.cfg['denoise_depth_use_octree_cloud']:
+                rays = self._denoise_rays(rays)
+            self.rays = torch.cat((self.rays, rays), dim=0).contiguous()     # stays on the device (the reference moves it to the CPU, :431)
+        self.data_loader = DataLoader(rays=self.rays, batch_size=self.cfg['N_rand'])
+        self._step_buf = None
+
+    # ------------------------------------------------------------------ the hot path
+    def _ensure_step_buffers(self, N):
+        if self._step_buf is not None and self._step_buf['N'] == N:
+            return self._step_buf
+        cfg, dev = self.cfg, self.device
+        S = cfg['N_samples'] + cfg['N_samples_around_depth']
+        F = len(self.images)
+        enc = self.models['embed_fn']
+        b = dict(N=N, S=S, F=F)
+        b['z_vals'] = torch.empty(N, S, device=dev)
+        b['tf'] = torch.empty(F, 12, device=dev)
+        b['grad_tf'] = torch.zeros(F, 12, device=dev)
+        b['losses'] = torch.zeros(8, device=dev)
+        b['march_err'] = torch.zeros(1, dtype=torch.int32, device=dev)
+        sb = ops.StepBuffers()
+        pa, fa = self.models['pose_array'], self.models['feature_array']
+        sb.set_scalars(N=N, S=S, L=enc.n_levels, C=2, F=F, ff=cfg['frame_features'], ray_dim=12, amp=int(bool(cfg['amp'])),
+                       S_log2=float(np.log2(enc.per_level_scale)), H=int(enc.base_resolution), need_pose_grad=int(pa is not None))
+        sb.set(offsets=self.offsets_dev, table_f32=self.table, table_f16=self.table_f16, mlp=self.mlp_flat,
+               feat=(fa.data.data if fa is not None else None), tf=b['tf'], z_vals=b['z_vals'],
+               loss_scale=(self.amp_scaler.state if self.amp_scaler.enabled else None), grad_table=self.adam_segs['table']['grad'],
+               grad_mlp=self.adam_segs['mlp']['grad'], grad_tf=b['grad_tf'],
+               grad_feat=(self.adam_segs['feat']['grad'] if fa is not None else None), losses=b['losses'],
+               found_inf=self.amp_scaler.found_inf)
+        ws = torch.zeros(max(sb.workspace_bytes(), 256), dtype=torch.uint8, device=dev)
+        sb.set(workspace=ws)
+        b['sb'] = sb
+        self._step_buf = b
+        return b
+
+    def _forward_backward(self, batch, t_rand=None, taps=None):
+        """Launches pose correction, ray march and the fused forward+loss+backward for `batch` [N,12]. Gradients accumulate into
+        the flat grad buffers (scaled by the loss scale); nothing synchronises."""
+        cfg = self.cfg
+        sc = cfg['sc_factor']
+        batch = batch.contiguous()
+        b = self._ensure_step_buffers(batch.shape[0])
+        sb = b['sb']
+        pa = self.models['pose_array']
+        trunc = self.get_truncation()
+        ops.pose_forward(pa.data.data if pa is not None else None, self.c2w_array, cfg['max_trans'] * sc, cfg['max_rot'], out=b['tf'])
+        ops.ray_march(batch, b['tf'], self.octree_m.occ_bits, self.octree_m.level, cfg['N_samples'], cfg['N_samples_around_depth'], trunc,
+                      cfg['near'] * sc, cfg['far'] * sc, cfg['neg_trunc_ratio'], t_rand=t_rand, perturb=bool(cfg.get('perturb', 1)),
+                      seed=0x5DEECE66D, offset=self.global_step, z_vals=b['z_vals'], err_flag=b['march_err'])
+        ops.fill_step_cfg(sb, cfg, trunc)
+        sb.set(rays=batch)
+        for k in ('rgb_map', 'raw', 'valid_samples', 'weights'):
+            sb.set(**{k: (taps.get(k) if taps else None)})
+        b['losses'].zero_()
+        if pa is not None:
+            b['grad_tf'].zero_()
+        sb.launch()
+        if pa is not None:
+            ops.pose_backward(pa.data.data, self.c2w_array, b['grad_tf'], self.adam_segs['pose']['grad'].view(-1, 6), cfg['max_trans'] * sc,
+                              cfg['max_rot'], self.amp_scaler.state if self.amp_scaler.enabled else None)
+        # host-side tiny terms (nerf_runner.py:743-752): feature regulariser, pose regulariser
+        fa = self.models['feature_array']
+        scale = self.amp_scaler.state[0] if self.amp_scaler.enabled else 1.0
+        if fa is not None and cfg['feature_reg_weight'] > 0:
+            self.adam_segs['feat']['grad'].add_(fa.data.data.view(-1) * (2.0 * cfg['feature_reg_weight'] / fa.data.numel() * scale))
+        if pa is not None and cfg.get('pose_reg_weight', 0) > 0:
+            d = pa.data.data[1:]
+            self.adam_segs['pose']['grad'].view(-1, 6)[1:].add_(d / d.norm().clamp(min=1e-12) * cfg['pose_reg_weight'])
+        return b
+
+    def _optimizer_step(self):
+        groups = self.optimizer.param_groups
+        segs = [dict(s, lr=groups[s['group']]['lr']) for s in self.adam_segs.values()]
+        ops.adam_step(segs, 0.9, 0.999, 1e-15, self.adam_step_count, self.amp_scaler.state if self.amp_scaler.enabled else None,
+                      self.amp_scaler.found_inf)
+
+    def train_loop(self, batch, t_rand=None):
+        """One train step (reference nerf_runner.py:679-852): forward, losses, backward, optimizer step, lr schedule."""
+        b = self._forward_backward(batch, t_rand=t_rand)
+        self._optimizer_step()
+        if self.global_step % 10 == 0 and self.global_step > 0:
+            self.schedule_lr()
+        cfg = self.cfg
+        if self.global_step % cfg['i_weights'] == 0 and self.global_step > 0:
+            self.save_weights(out_file=os.path.join(cfg['save_dir'], 'model_latest.pth'), models=self.models)
+        if self.global_step % cfg['i_print'] == 0:
+            logging.info(f'Iter: {self.global_step}, ' + ', '.join(f'{k}: {v:.7f}' for k, v in self.get_metrics().items()))
+        return b
+
+    def get_metrics(self):
+        """Loss terms of the LAST step with the reference's metric names (nerf_runner.py:794-815). Synchronises."""
+        l = self._step_buf['losses'].cpu().numpy()
+        m = {'loss': float(l[0]), 'rgb_loss': float(l[1]), 'rgb0_loss': 0.0, 'fs_rgb_loss': float(l[4]), 'depth_loss': 0.0, 'depth_loss0': 0.0,
+             'fs_loss': float(l[2]), 'point_cloud_loss': 0.0, 'point_cloud_normal_loss': 0.0, 'sdf_loss': float(l[3]), 'eikonal_loss': 0.0,
+             'variation_loss': 0.0, 'truncation(meter)': self.get_truncation() / self.cfg['sc_factor'],
+             'valid_samples': float(l[5]), 'valid_rays': float(l[6])}
+        fa = self.models['feature_array']
+        if fa is not None:
+            m['reg_features'] = float(self.cfg['feature_reg_weight'] * (fa.data.data ** 2).mean().item())
+            m['loss'] += m['reg_features']
+        if self.models['pose_array'] is not None:
+            m['pose_reg'] = float(self.cfg.get('pose_reg_weight', 0) * self.models['pose_array'].data.data[1:].norm().item())
+            m['loss'] += m['pose_reg']
+        return m
+
+    def train(self):
+        """nerf_runner.py:855-863."""
+        set_seed(0)
+        for it in range(self.N_iters):
+            if it % max(self.N_iters // 10, 1) == 0:
+                logging.info(f'train progress {it}/{self.N_iters}')
+            batch = next(self.data_loader)
+            self.train_loop(batch)
+            self.global_step += 1
+
+    # ------------------------------------------------------------------ evaluation helpers (downstream of the path)
+    @torch.no_grad()
+    def render(self, rays, ray_ids=None, frame_ids=None, depth=None, lindisp=False, perturb=False, raw_noise_std=0.0, get_normals=False,
+               near=None, far=None):
+        """Reference nerf_runner.py:1172-1198 contract: returns [rgb_map, extras] with extras['raw','z_vals','valid_samples',
+        'weights']. Evaluated by the fused kernel with taps; the gradients it also produces are discarded."""
+        N = rays.shape[0]
+        S = self.cfg['N_samples'] + self.cfg['N_samples_around_depth']
+        dev = self.device
+        taps = dict(rgb_map=torch.zeros(N, 3, device=dev), raw=torch.zeros(N, S, 4, device=dev),
+                    valid_samples=torch.zeros(N, S, dtype=torch.uint8, device=dev), weights=torch.zeros(N, S, device=dev))
+        saved_perturb = self.cfg.get('perturb', 1)
+        self.cfg['perturb'] = int(bool(perturb))
+        keep = {k: s['grad'].clone() for k, s in self.adam_segs.items()}
+        try:
+            b = self._forward_backward(rays, taps=taps)
+        finally:
+            self.cfg['perturb'] = saved_perturb
+        for k, s in self.adam_segs.items():
+            s['grad'].copy_(keep[k])
+        self.amp_scaler.found_inf.zero_()
+        extras = {'raw': taps['raw'], 'z_vals': b['z_vals'].clone(), 'valid_samples': taps['valid_samples'].bool(), 'weights': taps['weights']}
+        return [taps['rgb_map'], extras]
+
+    def _model_args(self):
+        return self._ensure_step_buffers(self.cfg['N_rand'])['sb']
+
+    @torch.no_grad()
+    def run_network_density(self, inputs, get_normals=False):
+        """nerf_runner.py:1307-1347 (SDF only): inputs [..,3] in normalised space -> sdf [..,1]."""
+        if get_normals:
+            raise NotImplementedError('normals from run_network_density are not built')
+        flat = inputs.reshape(-1, 3).float().contiguous().to(self.device)
+        sdf = ops.query_sdf(self._model_args(), flat)
+        return sdf.reshape(list(inputs.shape[:-1]) + [1]), torch.ones(len(flat), dtype=torch.bool, device=self.device)
+
+    @torch.no_grad()
+    def extract_mesh(self, level=None, voxel_size=0.003, isolevel=0.0, return_sigma=False):
+        """nerf_runner.py:1351-1409: SDF on a dense grid (only inside occupied cells), then marching cubes. The SDF sweep runs on
+        the native query kernel; marching cubes uses scikit-image when available (it is not in the build image: then only
+        `return_sigma=True` callers get a result and mesh is None)."""
+        vs = voxel_size * self.cfg['sc_factor']
+        bounds = np.array(self.cfg['bounding_box']).reshape(2, 3)
+        axes = [np.arange(bounds[0, i] + 0.5 * vs, bounds[1, i], vs) for i in range(3)]
+        Nx = len(axes[0])
+        grid = torch.tensor(np.stack(np.meshgrid(*axes, indexing='ij'), -1).astype(np.float32).reshape(-1, 3)).to(self.device)
+        valid = self.octree_m.get_center_ids(grid) >= 0 if self.octree_m is not None else torch.ones(len(grid), dtype=torch.bool, device=self.device)
+        sigma = torch.ones(len(grid), device=self.device)
+        if valid.any():
+            sigma[valid] = ops.query_sdf(self._model_args(), grid[valid].contiguous())
+        sigma = sigma.reshape(Nx, Nx, Nx).cpu().numpy()
+        mesh = None
+        try:
+            from skimage import measure
+            import trimesh
+            verts, tris, _, _ = measure.marching_cubes(sigma, isolevel)
+            step = np.array([a[-1] - a[0] for a in axes]) / np.array([len(a) - 1 for a in axes])
+            verts = step.reshape(1, 3) * verts + np.array([a[0] for a in axes]).reshape(1, 3)
+            mesh = trimesh.Trimesh(verts, tris, process=False)
+        except Exception as e:                      # same policy as the reference (:1390-1394): log and return None
+            logging.info(f'ERROR Marching Cubes {e}')
+        if return_sigma:
+            return mesh, sigma, grid
+        return mesh
+
+    # ------------------------------------------------------------------ checkpoints (nerf_runner.py:528-576)
+    def save_weights(self, out_file, models):
+        data = {'global_step': self.global_step, 'model': models['model'].state_dict(), 'optimizer': self.optimizer.state_dict(),
+                'embed_fn': models['embed_fn'].state_dict()}
+        if models.get('embeddirs_fn') is not None:
+            data['embeddirs_fn'] = models['embeddirs_fn'].state_dict()
+        if self.cfg['optimize_poses'] > 0:
+            data['pose_array'] = models['pose_array'].state_dict()
+        if self.cfg['frame_features'] > 0:
+            data['feature_array'] = models['feature_array'].state_dict()
+        if self.octree_m is not None:
+            data['octree'] = self.octree_m.octree
+        data['amp_scaler'] = self.amp_scaler.state_dict()
+        os.makedirs(os.path.dirname(out_file) or '.', exist_ok=True)
+        torch.save(data, out_file)
+        latest = f'{os.path.dirname(out_file)}/model_latest.pth'
+        if os.path.abspath(latest) != os.path.abspath(out_file):
+            import shutil
+            shutil.copyfile(out_file, latest)
+
+    def load_weights(self, ckpt_path):
+        ckpt = torch.load(ckpt_path, map_location=self.device, weights_only=False)
+        self.models['model'].load_state_dict(ckpt['model'])            # copies INTO the flat-buffer views
+        self.models['embed_fn'].load_state_dict(ckpt['embed_fn'])
+        if self.models['feature_array'] is not None:
+            self.models['feature_array'].load_state_dict(ckpt['feature_array'])
+        if self.models['pose_array'] is not None:
+            self.models['pose_array'].load_state_dict(ckpt['pose_array'])
+        if 'octree' in ckpt:
+            self.octree_m = OctreeManager(octree=ckpt['octree'], device=self.device)
+        if self.table_f16 is not None:
+            self.table_f16.copy_(self.table)
+        # optimizer moments: copy into the aliased flat buffers (keeps the kernels' pointers valid)
+        live = self.optimizer.state_dict()
+        saved = ckpt['optimizer']
+        id2p = {}
+        for g in self.optimizer.param_groups:
+            for p in g['params']:
+                id2p[len(id2p)] = p
+        for idx, st in saved['state'].items():
+            p = id2p[int(idx)]
+            mine = self.optimizer.state[p]
+            mine['exp_avg'].copy_(st['exp_avg'])
+            mine['exp_avg_sq'].copy_(st['exp_avg_sq'])
+            self.adam_step_count.fill_(int(torch.as_tensor(st['step']).item()))
+        for g, sg in zip(self.optimizer.param_groups, saved['param_groups']):
+            g['lr'] = sg['lr']
+        del live
+        self.global_step = int(ckpt.get('global_step', 0))
+        self._step_buf = None

@@ -36,6 +36,14 @@ def pack_occupancy(occ):
     return torch.from_numpy(words.view(np.int32).copy())
 
 
+def grid_level_scales(S, H, L, device='cuda'):
+    """Per-level `scale` as the device computes it (exp2f), float32 tensor [L]."""
+    lib = _lib.load()
+    out = torch.empty(L, device=device, dtype=torch.float32)
+    _lib.check(lib.nof_grid_level_scales(float(S), int(H), int(L), _lib.ptr(out), _lib.stream()), 'nof_grid_level_scales')
+    return out
+
+
 def pose_forward(pose_data, c2w, max_trans, max_rot_deg, out=None):
     lib = _lib.load()
     F = c2w.shape[0]

@@ -70,6 +70,10 @@ int nof_grid_encode_backward(const void* grad, const float* inputs, const void* 
                              uint32_t H, int calc_grad_inputs, const void* dy_dx, void* grad_inputs,
                              uint32_t gridtype, int align_corners, int dtype, nof_stream_t stream);
 
+/* Per-level geometry exactly as the device evaluates it (gridencoder.cu:155: scale = exp2f(level*S)*H - 1). CUDA's exp2f
+ * differs from a host libm by an ulp at some levels, so test oracles take the scales from here. scales_out: device [L]. */
+int nof_grid_level_scales(float S, uint32_t H, int L, float* scales_out, nof_stream_t stream);
+
 /* Replaces common.sampleRaysUniformOccupiedVoxels (mycuda/common.h:28, common.cu:41-125).
  *   z_in_out [N,I,2], z_sampled [N,S], z_vals [N,S] (written where the ray has intervals, else untouched).
  *   err_flag: optional device int32, set to 1 where the reference would print+spin (we clamp). */

@@ -67,12 +67,14 @@ def _grid_index(cx, cy, cz, hashmap_size, resolution):
     return index % hashmap_size
 
 
-def grid_encode(x01, embeddings, offsets, S, H, exact_fma=True, want_dydx=False):
+def grid_encode(x01, embeddings, offsets, S, H, exact_fma=True, want_dydx=False, scales=None):
     """x01 [B,3] in [0,1] (fp32), embeddings [sO,C], offsets int array [L+1].
     Returns out [B, L*C] (and dy_dx [B,L,3,C] = d out / d x01, gridencoder.cu:202-245).
     Differentiable w.r.t. embeddings and (through the interpolation weights) x01.
     exact_fma emulates the FMA contractions nvcc applies to the reference kernel so the fp32 forward is
-    bit-comparable with the compiled reference."""
+    bit-comparable with the compiled reference. scales: optional per-level `scale` values as evaluated on the
+    device (CUDA's exp2f differs from libm by an ulp at some levels; tests read them back from the GPU or from
+    the golden fixtures) — with them the fp32 forward is bit-identical to the compiled reference kernel."""
     B = x01.shape[0]
     L = len(offsets) - 1
     C = embeddings.shape[1]
@@ -82,6 +84,9 @@ def grid_encode(x01, embeddings, offsets, S, H, exact_fma=True, want_dydx=False)
     for l in range(L):
         hsize = int(offsets[l + 1] - offsets[l])
         scale, res = level_scale_res(l, S, H)
+        if scales is not None:
+            scale = np.float32(scales[l])
+            res = int(np.ceil(scale)) + 1
         if exact_fma and x01.dtype == torch.float32:
             pos = (x01.double() * float(scale) + 0.5).float()      # fmaf(x, scale, 0.5)
         else:

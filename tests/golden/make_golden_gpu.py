@@ -68,9 +68,11 @@ def main():
             gin = torch.zeros(B, 3, device=dev, dtype=dt)
             ge.grid_encode_backward(gy.to(dt).to(dev), x.to(dev), e, od, gemb, B, 3, 2, L, S, 16, True, dy, gin, 0, False)
             torch.cuda.synchronize()
+            from bundlesdf_b200 import ops
+            scales = ops.grid_level_scales(S, 16, L)
             nz = gemb.float().abs().sum(-1).nonzero().reshape(-1)
             sv(f'ref_gpu_grid_{tag}_{dn}.npz', L=L, finest=finest, log2T=log2T, table_seed=101, point_seed=102, grad_seed=103, B=B,
-               out=out, dy_dx=dy, grad_inputs=gin, grad_emb_idx=nz, grad_emb_val=gemb[nz])
+               out=out, dy_dx=dy, grad_inputs=gin, grad_emb_idx=nz, grad_emb_val=gemb[nz], scales=scales)
 
     # ---- 2. common.sampleRaysUniformOccupiedVoxels / postprocessOctreeRayTracing
     rng = np.random.default_rng(7)

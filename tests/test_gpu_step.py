@@ -13,7 +13,7 @@ from oracle import nof_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _oracle(scene, t_rand, half):
+def _oracle(scene, t_rand, half, z_vals=None):
     cfg, P = scene['cfg'], scene['params']
     P = dict(P)
     leaves = ['embeddings'] + [k for k in P if 'net' in k]
@@ -25,7 +25,7 @@ def _oracle(scene, t_rand, half):
         P[k] = P[k].detach().clone().requires_grad_(True)
     S_occ = cfg['N_samples']
     out = O.forward_step(P, scene['batch'], scene['c2w'], scene['occ'], cfg, t_rand_occ=None if t_rand is None else t_rand[:, :S_occ],
-                         t_rand_depth=None if t_rand is None else t_rand[:, S_occ:], half=half)
+                         t_rand_depth=None if t_rand is None else t_rand[:, S_occ:], half=half, z_vals=z_vals)
     out['loss'].backward()
     return out, P
 
@@ -72,11 +72,14 @@ def test_fused_step_matches_oracle(L, finest, log2T, S_occ, S_d, N, ff, kw, amp)
     scene = helpers.make_scene(n_frames=4, N=N, cfg=cfg, **kw)
     rng = np.random.default_rng(11)
     t_rand = rng.random((N, S_occ + S_d), dtype=np.float32)
-    ref, P = _oracle(scene, t_rand, half=amp)
     res = helpers.run_fused_step(scene, amp=amp, t_rand=t_rand, loss_scale=(1024.0 if amp else None))
+    # the samples come from the kernel's own per-frame transforms (test_ray_march_matches_oracle pins them bit-exactly
+    # given identical transforms); the oracle's torch se3 chain differs from the pose kernel in the last ulp
+    ref0, _ = _oracle(scene, t_rand, half=amp)
+    np.testing.assert_allclose(res['z_vals'].cpu().numpy(), ref0['z_vals'].numpy(), rtol=0, atol=2e-6)
+    ref, P = _oracle(scene, t_rand, half=amp, z_vals=res['z_vals'].cpu())
     scale = 1024.0 if amp else 1.0
     ftol, ltol, gtol = (3e-3, 5e-3, 3e-2) if amp else (2e-5, 1e-4, 2e-3)
-    np.testing.assert_array_equal(res['z_vals'].cpu().numpy(), ref['z_vals'].numpy())
     np.testing.assert_array_equal(res['valid_samples'].cpu().numpy().astype(bool), ref['valid_samples'].numpy())
     np.testing.assert_allclose(res['weights'].cpu().numpy(), ref['weights'].detach().numpy(), rtol=1e-4, atol=1e-7)
     assert _rel_max(res['raw'].cpu().numpy(), ref['raw'].detach().numpy()) < ftol
@@ -102,8 +105,8 @@ def test_fused_step_matches_oracle(L, finest, log2T, S_occ, S_d, N, ff, kw, amp)
 def test_fused_step_no_pose_optimisation():
     cfg = helpers.make_cfg(4, 128, 14, 32, 32, optimize_poses=0)
     scene = helpers.make_scene(n_frames=3, N=32, cfg=cfg)
-    ref, P = _oracle(scene, None, half=False)
     res = helpers.run_fused_step(scene, amp=False, t_rand=None)
+    ref, P = _oracle(scene, None, half=False, z_vals=res['z_vals'].cpu())
     assert _rel_max(res['grad_table'].cpu().numpy(), P['embeddings'].grad.numpy()) < 2e-3
     assert torch.all(res['grad_tf'] == 0)
 
