@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — Neural-Object-Field train-step throughput (BASELINE.json metric: NeRF train rays/s, steps/s, % HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C1|C3|C5]
+
+Workload (config.workload): BASELINE.json configs[1] "C2" — milk-jug-shaped synthetic sequence, 200 frames 640x480,
+2048 rays x 128 samples (64 occupied-voxel + 64 around-depth), hash grid L=16 T=2^19 finest 256, MLP = the reference
+NeRFSmall (SDF 2x64, colour 3x64), AMP on, pose refinement on. A step = one NerfRunner.train_loop (gather batch from the
+ray pool -> pose correction -> ray march -> fused forward/loss/backward -> pose backward -> Adam).
+  value : rays/s with the ray pool resident in HBM, CUDA-event timed over exactly K steps (max over ranks).
+  e2e   : same metric through the public API from HOST buffers: every step copies its batch from pinned host memory
+          (what the reference does after add_new_frames, nerf_runner.py:431: rays live on the CPU) and reads the loss back.
+  roofline : the fused step kernel alone, algorithmic bytes P*64*L*C + N*60 / its mean launch time.
+  cpu_baseline : the oracle port (oracle/nof_oracle.py, torch fp32 on all host cores) on a bounded sample.
+Multi-GPU (torchrun): one independent sequence per rank, NCCL only for barrier + gather of the timings ("weak" scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+CONFIGS = {
+    # name: frames, N_rand, S_occ, S_depth, L, finest, log2T, optimize_poses, pose_noise, frame_stride
+    'C1': dict(frames=1, N=1024, S_occ=32, S_d=32, L=4, finest=128, log2T=22, pose=0, noise=False, stride=1),
+    'C2': dict(frames=200, N=2048, S_occ=64, S_d=64, L=16, finest=256, log2T=19, pose=1, noise=False, stride=1),
+    'C3': dict(frames=20, N=4096, S_occ=64, S_d=64, L=16, finest=256, log2T=19, pose=1, noise=True, stride=50),
+    'C5': dict(frames=300, N=8192, S_occ=128, S_d=64, L=16, finest=512, log2T=22, pose=1, noise=False, stride=1),
+}
+WORKLOAD = {
+    'C1': 'C1: single 640x480 synthetic RGBD frame, 1024 rays x 64 samples, hash L=4, MLP 2x64/3x64',
+    'C2': 'C2: milk-jug synthetic sequence, 200 frames 640x480, 2048 rays x 128 samples, hash L=16 T=2^19, MLP 2x64/3x64, 1xB200',
+    'C3': 'C3: HO3D-shaped synthetic, 640x480, 1000-frame orbit, 20-frame memory pool, 4096 rays x 128 samples, pose refinement on',
+    'C5': 'C5: global-refine mode, 300 frames, 8192 rays x 192 samples, hash L=16 T=2^22',
+}
+
+
+def make_cfg(c):
+    from bundlesdf_b200 import synthetic as syn
+    return syn.default_cfg(N_rand=c['N'], N_samples=c['S_occ'], N_samples_around_depth=c['S_d'], num_levels=c['L'], finest_res=c['finest'],
+                           log2_hashmap_size=c['log2T'], optimize_poses=c['pose'], amp=True, n_step=2000, denoise_depth_use_octree_cloud=True)
+
+
+def algorithmic_bytes(c):
+    """64*L*C B/point with pose refinement (48*L*C without) + 60 B/ray."""
+    P = c['N'] * (c['S_occ'] + c['S_d'])
+    per_pt = (64 if c['pose'] else 48) * c['L'] * 2
+    return P * per_pt + c['N'] * 60
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        qs = ['clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap',
+              'clocks.sm,clocks.max.sm,clocks_throttle_reasons.hw_slowdown,clocks_throttle_reasons.hw_thermal_slowdown,'
+              'clocks_throttle_reasons.sw_thermal_slowdown,clocks_throttle_reasons.sw_power_cap',
+              'clocks.sm,clocks.max.sm']
+        qi = 0
+        self.error = None
+        while not self._stop_evt.is_set():
+            try:
+                r = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={qs[qi]}', '--format=csv,noheader,nounits'],
+                                   capture_output=True, text=True, timeout=5)
+                out = r.stdout.strip()
+                if r.returncode == 0 and out and 'not a valid' not in out.lower() and out[0].isdigit():
+                    self.rows.append([x.strip() for x in out.split(',')])
+                elif qi + 1 < len(qs):
+                    self.error = (out or r.stderr.strip())[:200]
+                    qi += 1
+                    continue
+                else:
+                    self.error = (out or r.stderr.strip())[:200]
+            except Exception as e:
+                self.error = repr(e)[:200]
+            self._stop_evt.wait(0.2)
+
+    def summary(self):
+        self._stop_evt.set()
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable'], 'error': getattr(self, 'error', None)}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.rows[0][1]) if self.rows[0][1].replace('.', '').isdigit() else None,
+                'reasons': reasons, 'samples': len(self.rows)}
+
+
+def build_runner(c, seed, device):
+    from bundlesdf_b200 import synthetic as syn
+    from bundlesdf_b200.nerf_runner import NerfRunner
+    total = c['frames'] * c['stride'] if c['stride'] > 1 else None
+    seq = syn.make_sequence(c['frames'], H=480, W=640, device=device, seed=seed, pose_noise=c['noise'], frame_stride=c['stride'], total_frames=total)
+    cfg = make_cfg(c)
+    cfg['sc_factor'] = seq['sc_factor']
+    cfg['translation'] = seq['translation'].tolist()
+    runner = NerfRunner(cfg, seq['images'], seq['depths'], seq['masks'], None, seq['poses'], seq['K'], build_octree_pcd=syn.PointCloud(seq['pcd_normalized']))
+    return runner, seq
+
+
+def rank_seed(base_seed, rank):
+    """Sequence seed of a rank: independent sequences, one per GPU."""
+    return int(base_seed) + int(rank)
+
+
+def aggregate_throughput(units_local, seconds_local, world, device='cpu'):
+    """Whole-job throughput = units processed by ALL ranks / MAX over ranks of the elapsed time. No data-path collective:
+    one all_reduce(MAX) of a scalar and one all_reduce(SUM) of the unit counts."""
+    if world == 1:
+        return units_local / seconds_local, seconds_local
+    import torch.distributed as dist
+    t = torch.tensor([seconds_local], dtype=torch.float64, device=device)
+    u = torch.tensor([float(units_local)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    return float(u.item()) / float(t.item()), float(t.item())
+
+
+def time_steps(fn, n):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(n):
+        fn()
+    ev1.record()
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1) / 1e3
+
+
+_CPU_SCENE = {}
+
+
+def _cpu_scene(c, seed):
+    from oracle import nof_oracle as O
+    from bundlesdf_b200 import synthetic as syn
+    n_frames = min(c['frames'], 8)
+    seq = syn.make_sequence(n_frames, H=480, W=640, device='cpu', seed=seed, pose_noise=c['noise'])
+    cfg = make_cfg(c)
+    cfg['sc_factor'] = seq['sc_factor']
+    rng = np.random.default_rng(seed)
+    K = seq['K']
+    rows = []
+    for f in range(n_frames):
+        vs, us = np.nonzero(seq['masks'][f, ..., 0])
+        sel = rng.choice(len(vs), size=min(len(vs), 4096), replace=False)
+        vs, us = vs[sel], us[sel]
+        r = np.zeros((len(vs), 12), np.float32)
+        r[:, 0] = (us - K[0, 2]) / K[0, 0]; r[:, 1] = -(vs - K[1, 2]) / K[1, 1]; r[:, 2] = -1
+        r[:, 3:6] = seq['images'][f, vs, us]; r[:, 6] = seq['depths'][f, vs, us, 0]; r[:, 7] = 1; r[:, 8] = f; r[:, 10] = 0.5; r[:, 11] = 8.0
+        rows.append(r)
+    pool = torch.from_numpy(np.concatenate(rows, 0))
+    occ, level = O.build_occupancy(seq['pcd_normalized'], cfg)
+    return seq, cfg, pool, occ, level, n_frames
+
+
+_CPU_THREADS = None
+
+
+def pick_cpu_threads(c):
+    """All host cores unless fewer are faster: the step is a chain of small torch ops whose OpenMP fork/join cost grows with the
+    thread count (128 threads on the GPU box are ~60x slower than 16 for this workload). One probe step per candidate."""
+    global _CPU_THREADS
+    if _CPU_THREADS is None:
+        n = os.cpu_count() or 1
+        best, best_t = n, None
+        for cand in sorted({n, max(1, n // 2), min(n, 32), min(n, 16), min(n, 8)}, reverse=True):
+            t, _ = cpu_baseline_run(c, 1, 0, 64, threads=cand)
+            if best_t is None or t < best_t:
+                best, best_t = cand, t
+        _CPU_THREADS = best
+    return _CPU_THREADS
+
+
+def cpu_baseline_run(c, steps, warmup, sample_rays, seed=0, threads=None):
+    """The oracle port timed on the host cores: full train step (sampling, encode, MLP, losses, backward, Adam) on
+    `sample_rays` rays of the workload per step."""
+    from oracle import nof_oracle as O
+    from bundlesdf_b200 import synthetic as syn
+    torch.set_num_threads(threads or pick_cpu_threads(c))
+    key = (c['frames'], c['noise'], seed)
+    if key not in _CPU_SCENE:
+        _CPU_SCENE[key] = _cpu_scene(c, seed)
+    seq, cfg, pool, occ, level, n_frames = _CPU_SCENE[key]
+    rng = np.random.default_rng(seed)
+    offsets, pls = O.grid_offsets(c['L'], 16, c['finest'], c['log2T'])
+    g = torch.Generator().manual_seed(seed)
+    P = {'embeddings': ((torch.rand(int(offsets[-1]), 2, generator=g) * 2 - 1) * 1e-4).requires_grad_(True), 'offsets': offsets,
+         'S': float(np.log2(pls)), 'H': 16}
+    for k, v in O.init_mlp(c['L'] * 2, 9, seed=seed).items():
+        P[k] = v.requires_grad_(True)
+    P['pose_data'] = torch.zeros(n_frames, 6, requires_grad=True) if c['pose'] else None
+    P['feature_data'] = None
+    leaves = [v for v in P.values() if torch.is_tensor(v) and v.requires_grad]
+    state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in leaves]
+    c2w = torch.from_numpy(seq['poses']).float()
+    S = c['S_occ'] + c['S_d']
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        ids = torch.from_numpy(rng.choice(len(pool), size=sample_rays, replace=False))
+        batch = pool[ids]
+        t_rand = rng.random((sample_rays, S), dtype=np.float32)
+        out = O.forward_step(P, batch, c2w, occ, cfg, t_rand_occ=t_rand[:, :c['S_occ']], t_rand_depth=t_rand[:, c['S_occ']:])
+        for p in leaves:
+            p.grad = None
+        out['loss'].backward()
+        with torch.no_grad():
+            for p, (m, v) in zip(leaves, state):
+                O.adam_update(p, p.grad, m, v, it + 1, 0.01)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return float(np.sum(times)), sample_rays * len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='C2', choices=list(CONFIGS))
+    ap.add_argument('--cpu-rays', type=int, default=256, help='rays per step of the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    c = CONFIGS[args.config]
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    S = c['S_occ'] + c['S_d']
+    config = {'workload': WORKLOAD[args.config], 'rays_per_step': c['N'], 'samples_per_ray': S, 'hash_levels': c['L'],
+              'log2_hashmap_size': c['log2T'], 'finest_res': c['finest'], 'frames': c['frames'], 'amp': True, 'optimize_poses': bool(c['pose']),
+              'parallelism': f'{world} independent sequence(s), one per GPU',
+              'l2_policy': 'inputs larger than L2 are not claimed: the fp16 table (17.4 MB at C2) is L2-resident by design; every step draws a '
+                           'fresh random batch from a >100 MB ray pool and the Adam pass streams ~300 MB per step, so no two timed steps reuse inputs'}
+
+    if args.impl == 'reference':
+        # The reference has no CPU implementation of this path (its grid encoder and samplers are CUDA-only, kaolin is absent):
+        # the reference arm is the oracle port on the host cores, on bounded samples of the same workload.
+        if rank != 0:
+            return
+        warm = max(1, min(args.warmup, 2))
+        steps = max(1, args.steps)
+        budget_s = 150.0
+        t_probe, _ = cpu_baseline_run(c, 1, 0, args.cpu_rays)
+        steps_fit = max(1, int(budget_s / max(t_probe, 1e-3)))
+        rays = args.cpu_rays
+        if steps > steps_fit:                      # keep exactly K steps, shrink the per-step sample instead
+            rays = max(8, int(args.cpu_rays * steps_fit / steps))
+        t, n_rays = cpu_baseline_run(c, steps, warm, rays)
+        v = n_rays / t
+        cores = pick_cpu_threads(c)
+        line = {'impl': 'reference', 'metric': 'nerf_train_rays_per_s', 'value': v, 'unit': 'rays/s', 'n_gpus': args.gpus, 'steps': steps,
+                'warmup': warm, 'ms_per_step': 1e3 * t / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+                                 'sample': f'{steps} full train steps (sample, encode, MLP, losses, backward, Adam) of {rays} rays x {S} samples each, torch fp32, {cores} of {os.cpu_count()} host threads (fastest of a probe)'},
+                'e2e': {'value': v, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+        print(json.dumps(line))
+        return
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    runner, seq = build_runner(c, seed=rank_seed(0, rank), device=dev)
+    N = c['N']
+
+    def step_resident():
+        batch = next(runner.data_loader)
+        runner.train_loop(batch)
+        runner.global_step += 1
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t = time_steps(step_resident, args.steps)
+    clocks = sampler.summary()
+    value, t = aggregate_throughput(N * args.steps, t, world, dev)
+
+    # ---- e2e: host-resident ray pool (pinned), per-step H2D of the batch and D2H of the loss
+    pool_host = runner.rays.cpu().pin_memory()
+    stage = torch.empty(N, 12).pin_memory()
+    loss_host = torch.empty(8).pin_memory()
+
+    def step_e2e():
+        ids = runner.data_loader.next_ids()             # device slice of the epoch permutation; batch_ray_ids is its CPU twin
+        torch.index_select(pool_host, 0, runner.data_loader.batch_ray_ids, out=stage)
+        batch = stage.to(dev, non_blocking=True)
+        b = runner.train_loop(batch)
+        loss_host.copy_(b['losses'], non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller reads the loss every step
+        runner.global_step += 1
+
+    for _ in range(3):
+        step_e2e()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(10, args.steps // 2)
+    t_e2e = time_steps(step_e2e, e2e_steps)
+    e2e_value, t_e2e = aggregate_throughput(N * e2e_steps, t_e2e, world, dev)
+
+    # ---- roofline of the dominant kernel (fused step), timed alone on its launch stream
+    batch = next(runner.data_loader)
+    runner._forward_backward(batch)
+    sb = runner._step_buf['sb']
+    for _ in range(3):
+        sb.launch()
+    n_k = 50
+    t_k = time_steps(sb.launch, n_k) / n_k
+    for s in runner.adam_segs.values():                 # the extra launches accumulated garbage gradients: clear them
+        s['grad'].zero_()
+    runner.amp_scaler.found_inf.zero_()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    abytes = algorithmic_bytes(c)
+    achieved = abytes / t_k / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(REPO, 'profiles', 'step_kernel_traffic.json'))).get(args.config)
+    except Exception:
+        pass
+    roofline = {'bound': 'hbm', 'kernel': 'step_amp_kernel (fused forward+loss+backward)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': traffic, 'algorithmic_bytes_per_launch': abytes, 'kernel_ms': t_k * 1e3,
+                'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s (of fallback)',
+                'note': 'algorithmic bytes assume no cache credit; the 17.4 MB fp16 table is L2-resident, so DRAM traffic is far below this'}
+
+    line = {'metric': 'nerf_train_rays_per_s', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': 1e3 * t / args.steps, 'steps_per_s': args.steps / t, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f16 (fp32 accumulate, fp32 master weights)', 'data': 'synthetic', 'config': config, 'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': N * 12 * 4, 'd2h_bytes_per_step': 32, 'steps': e2e_steps,
+                    'ms_per_step': 1e3 * t_e2e / e2e_steps},
+            'gpu_launches': 7 * args.steps, 'roofline': roofline, 'ray_pool': int(runner.rays.shape[0])}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        tc, nr = cpu_baseline_run(c, 3, 1, args.cpu_rays)
+        cores = pick_cpu_threads(c)
+        line['cpu_baseline'] = {'value': nr / tc, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+                                'sample': f'3 full train steps of {args.cpu_rays} rays x {S} samples (oracle port, torch fp32, {cores} of {os.cpu_count()} host threads, fastest of a probe) after 1 warm-up'}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -18,7 +18,7 @@ _vp, _i32, _u32, _u64, _f32, _sz, _i64 = C.c_void_p, C.c_int32, C.c_uint32, C.c_
 class NofMarchCfg(C.Structure):
     _fields_ = [('N', _i32), ('ray_dim', _i32), ('S_occ', _i32), ('S_depth', _i32), ('level', _i32), ('I_max', _i32),
                 ('trunc', _f32), ('near_sc', _f32), ('far_sc', _f32), ('neg_trunc_ratio', _f32), ('perturb', _i32),
-                ('seed', _u64), ('offset', _u64)]
+                ('seed', _u64), ('offset', _u64), ('offset_ptr', _vp)]
 
 
 class NofStep(C.Structure):
@@ -34,7 +34,7 @@ class NofStep(C.Structure):
 
 
 class NofAdamSeg(C.Structure):
-    _fields_ = [('param', _vp), ('grad', _vp), ('exp_avg', _vp), ('exp_avg_sq', _vp), ('shadow_f16', _vp), ('n', _sz), ('lr', _f32)]
+    _fields_ = [('param', _vp), ('grad', _vp), ('exp_avg', _vp), ('exp_avg_sq', _vp), ('shadow_f16', _vp), ('n', _sz), ('lr', _f32), ('lr_ptr', _vp)]
 
 
 _SIGS = {
@@ -54,7 +54,7 @@ _SIGS = {
     'nof_mlp_param_offsets': (C.c_int, [C.c_int, C.c_int, C.POINTER(_i32)]),
     'nof_step_workspace_bytes': (_sz, [C.POINTER(NofStep)]),
     'nof_step_fused': (C.c_int, [C.POINTER(NofStep), _vp]),
-    'nof_adam_step': (C.c_int, [C.POINTER(NofAdamSeg), C.c_int, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    'nof_adam_step': (C.c_int, [C.POINTER(NofAdamSeg), C.c_int, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     'nof_query_sdf': (C.c_int, [C.POINTER(NofStep), _vp, _vp, _i64, _vp]),
 }
 EXPORTS = tuple(_SIGS)

@@ -3,6 +3,8 @@
 // (grid.py:50-51 casts the whole fp32 table to fp16 every step) in ONE streaming pass:
 //   read g, m, v, p (16 B/param)  ->  write p, m, v, g=0 (16 B/param) + 2 B/param fp16 shadow.
 // HBM-bound by construction: 128-bit loads/stores, grid sized to a multiple of the SM count.
+#include <algorithm>
+
 #include "nof_common.cuh"
 
 namespace nof {
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(AdamArgs a, const in
     for (int k = 1; k < ADAM_MAX_SEGS; ++k) si += (k < a.n_segs && tile >= a.tile_begin[k]) ? 1 : 0;
     const NofAdamSeg sg = a.seg[si];
     const size_t base = (size_t)(tile - a.tile_begin[si]) * ADAM_TILE;
-    const float step_size = sg.lr * inv_bc1;
+    const float step_size = (sg.lr_ptr ? __ldg(sg.lr_ptr) : sg.lr) * inv_bc1;
 #pragma unroll
     for (int j = 0; j < ADAM_VEC_PER_THREAD; ++j) {
       const size_t i = base + ((size_t)j * ADAM_THREADS + threadIdx.x) * 4;
@@ -91,7 +93,8 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(AdamArgs a, const in
 }
 
 // GradScaler.update() (growth_factor 2, backoff 0.5, growth_interval 2000) + step counter + flag reset.
-__global__ void adam_finish_kernel(int32_t* step_ptr, float* scale_state, int32_t* found_inf) {
+__global__ void adam_finish_kernel(int32_t* step_ptr, float* scale_state, int32_t* found_inf, unsigned long long* tick) {
+  if (tick) *tick += 1ull;
   const bool inf = found_inf && (*found_inf != 0);
   if (!inf && step_ptr) *step_ptr += 1;
   if (scale_state) {
@@ -114,7 +117,7 @@ __global__ void adam_finish_kernel(int32_t* step_ptr, float* scale_state, int32_
 using namespace nof;
 
 extern "C" int nof_adam_step(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, float eps, int32_t* step,
-                             float* scale_state, int32_t* found_inf, nof_stream_t stream) {
+                             float* scale_state, int32_t* found_inf, uint64_t* tick, nof_stream_t stream) {
   NOF_REQUIRE(segs && n_segs >= 1 && n_segs <= ADAM_MAX_SEGS, "nof_adam_step: n_segs=%d (1..%d)", n_segs, ADAM_MAX_SEGS);
   AdamArgs a;
   a.n_segs = n_segs;
@@ -129,7 +132,7 @@ extern "C" int nof_adam_step(const NofAdamSeg* segs, int n_segs, float beta1, fl
                   "nof_adam_step: segment %d not 16-byte aligned", i);
       tiles += div_up<uint64_t>(segs[i].n, ADAM_TILE);
     } else {
-      a.seg[i] = NofAdamSeg{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0.f};
+      a.seg[i] = NofAdamSeg{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0.f, nullptr};
     }
   }
   a.tile_begin[ADAM_MAX_SEGS] = (uint32_t)tiles;
@@ -143,6 +146,6 @@ extern "C" int nof_adam_step(const NofAdamSeg* segs, int n_segs, float beta1, fl
     int rc = check_launch("adam_kernel");
     if (rc) return rc;
   }
-  adam_finish_kernel<<<1, 1, 0, st>>>(step, scale_state, found_inf);
+  adam_finish_kernel<<<1, 1, 0, st>>>(step, scale_state, found_inf, reinterpret_cast<unsigned long long*>(tick));
   return check_launch("adam_finish_kernel");
 }

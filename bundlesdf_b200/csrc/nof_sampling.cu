@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg
   float* io_t = s_io_all + (size_t)warp * I * 4;       // travel-time intervals
   float* io_z = io_t + (size_t)I * 2;                  // z intervals (scaled, clipped)
   const int S = cfg.S_occ + cfg.S_depth;
+  if (cfg.offset_ptr) cfg.offset += *cfg.offset_ptr;
 
   for (int r = blockIdx.x * MARCH_WARPS + warp; r < cfg.N; r += gridDim.x * MARCH_WARPS) {
     const float* row = rays + (size_t)r * cfg.ray_dim;

@@ -142,6 +142,11 @@ class NerfRunner:
         """nerf_runner.py:204-242: same modules, same creation order (=> same CPU-RNG initial weights for a given seed)."""
         device = device or self.device
         cfg = self.cfg
+        if cfg.get('eikonal_weight', 0) > 0:
+            raise NotImplementedError('eikonal_weight>0: the term is non-functional in the reference (train_loop renders with '
+                                      'get_normals=False, nerf_runner.py:686 -> KeyError at :736); not built yet (DESIGN.md row a15)')
+        if cfg.get('depth_weight', 0) > 0:
+            raise NotImplementedError('depth_weight>0: dead code in the reference (uses an undefined `depth`, nerf_runner.py:718)')
         if cfg['N_importance'] > 0:
             raise NotImplementedError('N_importance>0: dead code in the reference (nerf_runner.py:1106 unpacks 3 values into 2)')
         if not cfg['use_viewdirs']:
@@ -199,6 +204,12 @@ class NerfRunner:
         dev = self.device
         z = lambda t: torch.zeros_like(t)
         self.adam_step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        # device-resident step state so that a captured CUDA graph of the step never needs new launch arguments:
+        # learning rates (one per param group) and the RNG tick the sampler adds to its Philox offset
+        self.lr_dev = torch.tensor([g['lr'] for g in groups], dtype=torch.float32, device=dev)
+        self.tick = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._graph = None
+        self._eager_steps = 0
         segs = [dict(name='table', param=self.table.view(-1), grad=z(self.table).view(-1), exp_avg=z(self.table).view(-1),
                      exp_avg_sq=z(self.table).view(-1), shadow_f16=(self.table_f16.view(-1) if self.table_f16 is not None else None), group=0),
                 dict(name='mlp', param=self.mlp_flat, grad=z(self.mlp_flat), exp_avg=z(self.mlp_flat), exp_avg_sq=z(self.mlp_flat), group=0)]
@@ -209,6 +220,8 @@ class NerfRunner:
         if pa is not None:
             segs.append(dict(name='pose', param=pa.data.data.view(-1), grad=z(pa.data.data).view(-1), exp_avg=z(pa.data.data).view(-1),
                              exp_avg_sq=z(pa.data.data).view(-1), group=1))
+        for s in segs:
+            s['lr_ptr'] = self.lr_dev.data_ptr() + 4 * s['group']
         self.adam_segs = {s['name']: s for s in segs}
         # expose .grad and optimizer.state as views of the flat buffers (checkpoint / inspection parity)
         enc, model = self.models['embed_fn'], self.models['model']
@@ -233,6 +246,7 @@ class NerfRunner:
         """nerf_runner.py:579-583."""
         for i, g in enumerate(self.optimizer.param_groups):
             g['lr'] = self.param_groups_init[i]['lr'] * (self.cfg['decay_rate'] ** (float(self.global_step) / self.N_iters))
+        self.lr_dev.copy_(torch.tensor([g['lr'] for g in self.optimizer.param_groups], dtype=torch.float32))
 
     def get_truncation(self):
         """nerf_runner.py:663-676."""
@@ -371,6 +385,7 @@ class NerfRunner:
             self.rays = torch.cat((self.rays, rays), dim=0).contiguous()     # stays on the device (the reference moves it to the CPU, :431)
         self.data_loader = DataLoader(rays=self.rays, batch_size=self.cfg['N_rand'])
         self._step_buf = None
+        self._graph = None
 
     # ------------------------------------------------------------------ the hot path
     def _ensure_step_buffers(self, N):
@@ -415,7 +430,7 @@ class NerfRunner:
         ops.pose_forward(pa.data.data if pa is not None else None, self.c2w_array, cfg['max_trans'] * sc, cfg['max_rot'], out=b['tf'])
         ops.ray_march(batch, b['tf'], self.octree_m.occ_bits, self.octree_m.level, cfg['N_samples'], cfg['N_samples_around_depth'], trunc,
                       cfg['near'] * sc, cfg['far'] * sc, cfg['neg_trunc_ratio'], t_rand=t_rand, perturb=bool(cfg.get('perturb', 1)),
-                      seed=0x5DEECE66D, offset=self.global_step, z_vals=b['z_vals'], err_flag=b['march_err'])
+                      seed=0x5DEECE66D, offset=0, offset_ptr=self.tick, z_vals=b['z_vals'], err_flag=b['march_err'])
         ops.fill_step_cfg(sb, cfg, trunc)
         sb.set(rays=batch)
         for k in ('rgb_map', 'raw', 'valid_samples', 'weights'):
@@ -441,12 +456,48 @@ class NerfRunner:
         groups = self.optimizer.param_groups
         segs = [dict(s, lr=groups[s['group']]['lr']) for s in self.adam_segs.values()]
         ops.adam_step(segs, 0.9, 0.999, 1e-15, self.adam_step_count, self.amp_scaler.state if self.amp_scaler.enabled else None,
-                      self.amp_scaler.found_inf)
+                      self.amp_scaler.found_inf, tick=self.tick)
+
+    def _graph_usable(self, t_rand):
+        return (t_rand is None and bool(self.cfg.get('use_cuda_graph', True)) and self.cfg.get('trunc_decay_type', '') == '')
+
+    def _step_graphed(self, batch):
+        """Replay (capturing it on first use) a CUDA graph of the whole step: pose correction, ray march, fused
+        forward/loss/backward, pose backward, Adam. Every launch argument is static: the batch lives in a fixed buffer, the
+        learning rates, loss scale, Adam step and RNG tick live in device memory."""
+        g = self._graph
+        if g is None or g['N'] != batch.shape[0]:
+            if self._eager_steps < 2:                       # first steps run eagerly (buffer allocation, kernel attributes)
+                self._eager_steps += 1
+                self._forward_backward(batch)
+                self._optimizer_step()
+                return self._step_buf
+            static = torch.empty_like(batch)
+            static.copy_(batch)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self._forward_backward(static)
+                self._optimizer_step()
+            self._graph = g = dict(N=batch.shape[0], graph=graph, batch=static, buf=self._step_buf)
+        elif batch.data_ptr() != g['batch'].data_ptr():
+            g['batch'].copy_(batch)
+        g['graph'].replay()
+        self._step_buf = g['buf']                           # the buffers the graph writes (a render() may have swapped them)
+        return g['buf']
+
+    def step_batch_buffer(self):
+        """The static batch buffer of the captured step (gather straight into it to skip one copy), or None."""
+        return self._graph['batch'] if self._graph is not None else None
 
     def train_loop(self, batch, t_rand=None):
         """One train step (reference nerf_runner.py:679-852): forward, losses, backward, optimizer step, lr schedule."""
-        b = self._forward_backward(batch, t_rand=t_rand)
-        self._optimizer_step()
+        if self._graph_usable(t_rand):
+            b = self._step_graphed(batch)
+        else:
+            b = self._forward_backward(batch, t_rand=t_rand)
+            self._optimizer_step()
         if self.global_step % 10 == 0 and self.global_step > 0:
             self.schedule_lr()
         cfg = self.cfg
@@ -478,7 +529,11 @@ class NerfRunner:
         for it in range(self.N_iters):
             if it % max(self.N_iters // 10, 1) == 0:
                 logging.info(f'train progress {it}/{self.N_iters}')
-            batch = next(self.data_loader)
+            buf = self.step_batch_buffer()
+            if buf is not None:                               # gather straight into the captured step's input buffer
+                batch = ops.gather_rays(self.rays, self.data_loader.next_ids().contiguous(), out=buf)
+            else:
+                batch = next(self.data_loader)
             self.train_loop(batch)
             self.global_step += 1
 
@@ -597,3 +652,4 @@ class NerfRunner:
         del live
         self.global_step = int(ckpt.get('global_step', 0))
         self._step_buf = None
+        self._graph = None

@@ -69,7 +69,7 @@ def gather_rays(pool, ids, out=None):
 
 
 def ray_march(rays, tf, occ_bits, level, S_occ, S_depth, trunc, near_sc, far_sc, neg_trunc_ratio, t_rand=None, perturb=True,
-              seed=0, offset=0, I_max=None, z_vals=None, want_intervals=False, err_flag=None):
+              seed=0, offset=0, I_max=None, z_vals=None, want_intervals=False, err_flag=None, offset_ptr=None):
     lib = _lib.load()
     N, D = rays.shape
     if I_max is None:
@@ -79,7 +79,7 @@ def ray_march(rays, tf, occ_bits, level, S_occ, S_depth, trunc, near_sc, far_sc,
         z_vals = torch.empty(N, S, device=rays.device, dtype=torch.float32)
     inter = torch.empty(N, I_max, 2, device=rays.device, dtype=torch.float32) if want_intervals else None
     cfg = NofMarchCfg(N, D, S_occ, S_depth, level, I_max, float(trunc), float(near_sc), float(far_sc), float(neg_trunc_ratio),
-                      int(bool(perturb)), int(seed), int(offset))
+                      int(bool(perturb)), int(seed), int(offset), _lib.ptr(offset_ptr))
     _lib.check(lib.nof_ray_march(C.byref(cfg), _lib.ptr(rays), _lib.ptr(tf), _lib.ptr(occ_bits), _lib.ptr(t_rand), _lib.ptr(z_vals),
                                  _lib.ptr(inter), _lib.ptr(err_flag), _lib.stream()), 'nof_ray_march')
     return (z_vals, inter) if want_intervals else z_vals
@@ -118,16 +118,16 @@ def fill_step_cfg(sb, cfg, trunc):
     sb.set_scalars(**{k: float(cfg.get(k, 0)) for k in LOSS_CFG_KEYS})
 
 
-def adam_step(segs, beta1, beta2, eps, step, scale_state=None, found_inf=None):
+def adam_step(segs, beta1, beta2, eps, step, scale_state=None, found_inf=None, tick=None):
     """segs: list of dict(param, grad, exp_avg, exp_avg_sq, shadow_f16|None, lr). step: device int32 tensor [1]."""
     lib = _lib.load()
     arr = (NofAdamSeg * len(segs))()
     for i, s in enumerate(segs):
         n = s['param'].numel()
         arr[i] = NofAdamSeg(_lib.ptr(s['param']), _lib.ptr(s['grad']), _lib.ptr(s['exp_avg']), _lib.ptr(s['exp_avg_sq']),
-                            _lib.ptr(s.get('shadow_f16')), n, float(s['lr']))
+                            _lib.ptr(s.get('shadow_f16')), n, float(s['lr']), s.get('lr_ptr'))
     _lib.check(lib.nof_adam_step(arr, len(segs), float(beta1), float(beta2), float(eps), _lib.ptr(step), _lib.ptr(scale_state),
-                                 _lib.ptr(found_inf), _lib.stream()), 'nof_adam_step')
+                                 _lib.ptr(found_inf), _lib.ptr(tick), _lib.stream()), 'nof_adam_step')
 
 
 def query_sdf(sb, x, out=None):

@@ -119,6 +119,7 @@ typedef struct {
   float neg_trunc_ratio;
   int perturb;          /* 1: stratified jitter */
   uint64_t seed, offset;/* Philox counter RNG (used when t_rand == NULL && perturb) */
+  const uint64_t* offset_ptr; /* optional DEVICE counter added to `offset` (keeps the launch arguments static under CUDA graphs) */
 } NofMarchCfg;
 
 /* Replaces OctreeManager.ray_trace (Utils.py:443-475: kaolin unbatched_raytrace + unique_consecutive +
@@ -193,6 +194,7 @@ typedef struct {
   void* shadow_f16;     /* optional fp16 copy refreshed in the same pass (grid.py:50-51 cast), or NULL */
   size_t n;
   float lr;
+  const float* lr_ptr;  /* optional DEVICE scalar overriding `lr` (lr schedule without re-capturing a CUDA graph) */
 } NofAdamSeg;
 
 /* Replaces optimizer.zero_grad() + GradScaler.unscale/inf-check/step/update + torch.optim.Adam.step
@@ -200,9 +202,10 @@ typedef struct {
  * read g,m,v,p -> write p,m,v,(fp16 shadow) and zero g. Skips the update when *found_inf != 0.
  *   step: 1-based Adam step count held in a device int32 (incremented inside unless the step is skipped)
  *   scale_state: device float[2] = {loss_scale, growth_tracker} updated like GradScaler (init 65536,
- *                x2 every 2000 clean steps, x0.5 on inf) or NULL when amp is off. */
+ *                x2 every 2000 clean steps, x0.5 on inf) or NULL when amp is off.
+ *   tick: optional device uint64 incremented on EVERY call (feeds NofMarchCfg.offset_ptr). */
 int nof_adam_step(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, float eps, int32_t* step,
-                  float* scale_state, int32_t* found_inf, nof_stream_t stream);
+                  float* scale_state, int32_t* found_inf, uint64_t* tick, nof_stream_t stream);
 
 /* SDF-only inference for mesh extraction (run_network_density, nerf_runner.py:1307-1347 with
  * NeRFSmall.forward_sdf nerf_helpers.py:296-302): x [P,3] in [-1,1] (clipped inside) -> sdf [P]. */

@@ -1,0 +1,133 @@
+"""GPU: the NerfRunner drop-in (reference API surface) end to end on a small synthetic sequence."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import nof_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _runner(amp, n_frames=5, N=256, ff=0, **over):
+    from bundlesdf_b200 import synthetic as syn
+    from bundlesdf_b200.nerf_runner import NerfRunner
+    seq = syn.make_sequence(n_frames, H=120, W=160, device='cuda', seed=3, pose_noise=True)
+    cfg = syn.default_cfg(N_rand=N, N_samples=64, N_samples_around_depth=64, num_levels=16, finest_res=256, log2_hashmap_size=14, amp=amp,
+                          sc_factor=seq['sc_factor'], translation=seq['translation'].tolist(), n_step=60, frame_features=ff, **over)
+    r = NerfRunner(cfg, seq['images'], seq['depths'], seq['masks'], None, seq['poses'], seq['K'], build_octree_pcd=syn.PointCloud(seq['pcd_normalized']))
+    return r, seq
+
+
+@pytest.mark.parametrize('amp', [True, False])
+def test_single_step_gradients_match_oracle_through_runner(amp):
+    r, seq = _runner(amp, ff=2)
+    with torch.no_grad():
+        r.models['embed_fn'].embeddings.uniform_(-0.3, 0.3)
+        if r.table_f16 is not None:
+            r.table_f16.copy_(r.table)
+        r.models['pose_array'].data.normal_(0, 0.1)
+    batch = next(r.data_loader)
+    N, S = batch.shape[0], 128
+    t_rand = torch.rand(N, S, device='cuda')
+    b = r._forward_backward(batch, t_rand=t_rand)
+    torch.cuda.synchronize()
+    scale = r.amp_scaler.get_scale()
+    # oracle on the runner's own parameters
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in r.models['model'].state_dict().items()}
+    P = dict(sd)
+    P['embeddings'] = r.models['embed_fn'].embeddings.detach().cpu().clone().requires_grad_(True)
+    P['offsets'] = r.models['embed_fn'].offsets.cpu().numpy()
+    P['S'] = float(np.log2(r.models['embed_fn'].per_level_scale)); P['H'] = 16
+    P['pose_data'] = r.models['pose_array'].data.detach().cpu().clone().requires_grad_(True)
+    P['feature_data'] = r.models['feature_array'].data.detach().cpu().clone().requires_grad_(True)
+    ref = O.forward_step(P, batch.cpu(), r.c2w_array.cpu(), r.octree_m.occ.cpu().numpy(), r.cfg, half=amp, z_vals=b['z_vals'].cpu())
+    ref['loss'].backward()
+    gtol = 3e-2 if amp else 2e-3
+    rel = lambda a, w: np.abs(a - w).max() / max(np.abs(w).max(), 1e-30)
+    assert rel(r.models['embed_fn'].embeddings.grad.cpu().numpy() / scale, P['embeddings'].grad.numpy()) < gtol
+    for k, p in r.models['model'].named_parameters():
+        assert rel(p.grad.cpu().numpy() / scale, sd[k].grad.numpy()) < gtol, k
+    assert rel(r.models['pose_array'].data.grad.cpu().numpy(), P['pose_data'].grad.numpy()) < 2 * gtol
+    assert rel(r.models['feature_array'].data.grad.cpu().numpy() / scale, P['feature_data'].grad.numpy()) < gtol
+    m = r.get_metrics()
+    assert abs(m['loss'] - float(ref['loss'].detach())) <= (5e-3 if amp else 2e-4) * abs(float(ref['loss'].detach()))
+
+
+@pytest.mark.parametrize('amp', [True, False])
+def test_training_reduces_loss_and_recovers_geometry(amp):
+    r, seq = _runner(amp, n_frames=6, N=512)
+    r.cfg['i_print'] = 999999
+    losses = []
+    for it in range(120):
+        r.train_loop(next(r.data_loader))
+        r.global_step += 1
+        if it in (0, 119):
+            losses.append(r.get_metrics())
+    assert np.isfinite(losses[1]['loss'])
+    geo0 = losses[0]['sdf_loss'] + losses[0]['fs_loss']
+    geo1 = losses[1]['sdf_loss'] + losses[1]['fs_loss']
+    assert geo1 < 0.2 * geo0, (geo0, geo1)
+    assert losses[1]['rgb_loss'] < losses[0]['rgb_loss'] and losses[1]['loss'] < 0.6 * losses[0]['loss'], \
+        {k: (losses[0][k], losses[1][k]) for k in ('loss', 'rgb_loss', 'fs_loss', 'sdf_loss')}
+    # SDF sign: a point at the object's centre must be inside (negative), a far corner of an occupied cell positive-ish
+    sdf, _ = r.run_network_density(torch.tensor([[0.0, 0.0, 0.0]], device='cuda'))
+    assert sdf.item() < 0.0
+    assert r.adam_step_count.item() == 120
+    assert r.amp_scaler.found_inf.item() == 0
+
+
+def test_train_api_and_checkpoint_roundtrip(tmp_path):
+    r, seq = _runner(True, n_frames=4, N=256)
+    r.cfg['n_step'] = 12
+    r.N_iters = 13
+    r.cfg['save_dir'] = str(tmp_path)
+    r.train()                                    # reference API: n_step+1 iterations (nerf_runner.py:855-863)
+    assert r.global_step == 13
+    ck = os.path.join(tmp_path, 'model_latest.pth')
+    r.save_weights(ck, r.models)
+    before = {k: v.clone() for k, v in r.models['model'].state_dict().items()}
+    emb = r.models['embed_fn'].embeddings.detach().clone()
+    mats = r.models['pose_array'].get_matrices(np.arange(4))
+    assert mats.shape == (4, 4, 4) and torch.allclose(mats[0], torch.eye(4, device='cuda'))
+    r2, _ = _runner(True, n_frames=4, N=256)
+    r2.load_weights(ck)
+    for k, v in r2.models['model'].state_dict().items():
+        assert torch.equal(v, before[k])
+    assert torch.equal(r2.models['embed_fn'].embeddings.detach(), emb)
+    assert torch.equal(r2.table_f16, emb.half())
+    assert r2.adam_step_count.item() == r.adam_step_count.item()
+    # the two runners now take the same next step
+    batch = next(r.data_loader)
+    t_rand = torch.rand(batch.shape[0], 128, device='cuda')
+    r.train_loop(batch, t_rand=t_rand); r2.global_step = r.global_step; r2.train_loop(batch, t_rand=t_rand)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(r2.mlp_flat.cpu().numpy(), r.mlp_flat.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    ckpt = torch.load(ck, weights_only=False)
+    assert set(['model', 'embed_fn', 'pose_array', 'optimizer', 'global_step', 'octree']) <= set(ckpt.keys())
+    assert set(ckpt['embed_fn'].keys()) == {'embeddings', 'offsets'} and set(ckpt['pose_array'].keys()) == {'data'}
+
+
+def test_add_new_frames_and_extract_sigma():
+    from bundlesdf_b200 import synthetic as syn
+    r, seq = _runner(True, n_frames=3, N=256)
+    n0 = r.rays.shape[0]
+    seq2 = syn.make_sequence(5, H=120, W=160, device='cuda', seed=3, pose_noise=True, sc_factor=seq['sc_factor'])
+    r.add_new_frames(seq2['images'][3:], seq2['depths'][3:], seq2['masks'][3:], None, seq2['poses'], new_pcd=syn.PointCloud(seq2['pcd_normalized']))
+    assert r.rays.shape[0] > n0 and r.rays.is_cuda and len(r.images) == 5
+    assert r.models['pose_array'].data.shape[0] == 5
+    for _ in range(5):
+        r.train_loop(next(r.data_loader)); r.global_step += 1
+    mesh, sigma, pts = r.extract_mesh(voxel_size=0.02, return_sigma=True)
+    assert sigma.ndim == 3 and np.isfinite(sigma).all()
+
+
+def test_render_contract():
+    r, _ = _runner(False, n_frames=3, N=128)
+    batch = next(r.data_loader)
+    rgb, extras = r.render(batch, depth=batch[:, 6], perturb=False)
+    assert rgb.shape == (128, 3) and extras['raw'].shape == (128, 128, 4) and extras['z_vals'].shape == (128, 128)
+    assert extras['valid_samples'].dtype == torch.bool
+    assert float(r.adam_segs['table']['grad'].abs().max()) == 0.0

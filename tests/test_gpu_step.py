@@ -1,6 +1,6 @@
 """GPU parity of the fused path (pose -> ray march -> fused forward+loss+backward) against the CPU oracle with exact
 autograd gradients, at sizes the oracle finishes in seconds. Tolerances are stated per mode:
-  fp32 policy (cfg amp: false): forward <= 2e-5 rel, losses <= 1e-4 rel, gradients <= 2e-3 of the tensor's max |g|
+  fp32 policy (cfg amp: false): forward <= 1e-4 rel, losses <= 2e-4 rel, gradients <= 2e-3 of the tensor's max |g|
   AMP  policy (cfg amp: true) : compared with the oracle run with fp16 operand rounding; forward <= 3e-3,
                                  losses <= 5e-3 rel, gradients <= 3e-2 of max |g|."""
 import numpy as np
@@ -79,7 +79,7 @@ def test_fused_step_matches_oracle(L, finest, log2T, S_occ, S_d, N, ff, kw, amp)
     np.testing.assert_allclose(res['z_vals'].cpu().numpy(), ref0['z_vals'].numpy(), rtol=0, atol=2e-6)
     ref, P = _oracle(scene, t_rand, half=amp, z_vals=res['z_vals'].cpu())
     scale = 1024.0 if amp else 1.0
-    ftol, ltol, gtol = (3e-3, 5e-3, 3e-2) if amp else (2e-5, 1e-4, 2e-3)
+    ftol, ltol, gtol = (3e-3, 5e-3, 3e-2) if amp else (1e-4, 2e-4, 2e-3)
     np.testing.assert_array_equal(res['valid_samples'].cpu().numpy().astype(bool), ref['valid_samples'].numpy())
     np.testing.assert_allclose(res['weights'].cpu().numpy(), ref['weights'].detach().numpy(), rtol=1e-4, atol=1e-7)
     assert _rel_max(res['raw'].cpu().numpy(), ref['raw'].detach().numpy()) < ftol

@@ -46,7 +46,7 @@ def test_argument_validation_without_gpu():
     lib = _lib.load()
     assert lib.nof_grid_encode_forward(None, None, None, None, 1, 3, 2, 16, 0.5, 16, 0, None, 0, 0, 0, None) == -1
     assert b'null pointer' in lib.nof_last_error()
-    assert lib.nof_adam_step(None, 0, 0.9, 0.999, 1e-15, None, None, None, None) == -1
+    assert lib.nof_adam_step(None, 0, 0.9, 0.999, 1e-15, None, None, None, None, None) == -1
     with pytest.raises(_lib.NofError):
         _lib.ptr(torch.zeros(3))            # CPU tensor: the product path has no CPU fallback
 
