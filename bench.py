@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons, 'samples': len(self.rows)}
 
 
-def build_runner(c, seed, device):
+def build_runner(c, seed, device, eager=False):
     from bundlesdf_b200 import synthetic as syn
     from bundlesdf_b200.nerf_runner import NerfRunner
     total = c['frames'] * c['stride'] if c['stride'] > 1 else None
@@ -107,6 +107,7 @@ def build_runner(c, seed, device):
     cfg = make_cfg(c)
     cfg['sc_factor'] = seq['sc_factor']
     cfg['translation'] = seq['translation'].tolist()
+    cfg['use_cuda_graph'] = not eager
     runner = NerfRunner(cfg, seq['images'], seq['depths'], seq['masks'], None, seq['poses'], seq['K'], build_octree_pcd=syn.PointCloud(seq['pcd_normalized']))
     return runner, seq
 
@@ -235,6 +236,8 @@ def main():
     ap.add_argument('--config', default='C2', choices=list(CONFIGS))
     ap.add_argument('--cpu-rays', type=int, default=256, help='rays per step of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-range', action='store_true', help='bracket the timed steps with cudaProfilerStart/Stop (for ncu)')
+    ap.add_argument('--eager', action='store_true', help='disable CUDA-graph replay of the step (launch the kernels one by one)')
     args = ap.parse_args()
     c = CONFIGS[args.config]
     rank = int(os.environ.get('RANK', 0))
@@ -277,7 +280,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
-    runner, seq = build_runner(c, seed=rank_seed(0, rank), device=dev)
+    runner, seq = build_runner(c, seed=rank_seed(0, rank), device=dev, eager=args.eager)
     N = c['N']
 
     def step_resident():
@@ -292,7 +295,11 @@ def main():
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    if args.profile_range:                      # ncu --profile-from-start off: capture only the steady-state steps
+        torch.cuda.cudart().cudaProfilerStart()
     t = time_steps(step_resident, args.steps)
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.summary()
     value, t = aggregate_throughput(N * args.steps, t, world, dev)
 

@@ -9,7 +9,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'lib', 'libnof_sm100.so')
+LIB_PATH = os.environ.get('NOF_LIB', os.path.join(HERE, 'lib', 'libnof_sm100.so'))   # NOF_LIB: load a tuning variant
 
 NOF_F32, NOF_F16 = 0, 1
 _vp, _i32, _u32, _u64, _f32, _sz, _i64 = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_float, C.c_size_t, C.c_int64

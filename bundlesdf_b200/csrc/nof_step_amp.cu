@@ -9,7 +9,17 @@
 // (nerf_runner.py:1083-1088,1227-1304,1132-1169,679-758; grid.py:34-99; gridencoder.cu:107-365).
 #include "nof_step_common.cuh"
 
+#ifndef NOF_GATHER_UNROLL
+#define NOF_GATHER_UNROLL 2      // levels of the multires gather in flight per thread (8 x 4-byte loads each); measured on
+                                 // B200 (profiles/README.md): 2 -> 334 us, 4 -> 398 us, 8 -> 443 us per C2 launch
+#endif
+#ifndef NOF_STAGGER_NS
+#define NOF_STAGGER_NS 0         // >0: odd CTAs start late so the two CTAs of an SM alternate gather / MLP phases
+#endif
+
 namespace nof {
+
+constexpr int kGatherUnroll = NOF_GATHER_UNROLL;
 
 // ------------------------------------------------------------------------------------------------
 // tensor-core / ldmatrix / TMA primitives
@@ -280,6 +290,9 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(co
   __half2* Jslot = reinterpret_cast<__half2*>(a.p.workspace) + (size_t)blockIdx.x * (MAX_L * 3) * T;
   const int g8 = lane >> 2, t4 = lane & 3;
 
+#if NOF_STAGGER_NS > 0
+  if (blockIdx.x >= gridDim.x / 2) __nanosleep(NOF_STAGGER_NS);
+#endif
   for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
     // ============ 1. ray setup
     if (tid < R) setup_ray(sRay[tid], a, grp * R + tid);
@@ -308,7 +321,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(co
       for (int j = 0; j < KC; ++j) xc[j] = __float2half_rn(j < V ? rs.views[j] : 0.f);
       __half* x0 = X0 + (size_t)tid * LDX0;
       if (valid) {
-#pragma unroll 2
+#pragma unroll kGatherUnroll
         for (int l = 0; l < L; ++l) {
           float enc[2], J[3][2];
           if (a.p.need_pose_grad) {

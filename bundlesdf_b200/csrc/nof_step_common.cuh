@@ -68,6 +68,7 @@ struct LevelS {
   uint32_t hsize[MAX_L];
   uint32_t off[MAX_L];
   uint32_t dense[MAX_L];
+  uint32_t hmask[MAX_L];        // hsize-1 when hsize is a power of two (always for hashed levels built by grid.py), else 0
 };
 
 __device__ __forceinline__ void init_levels(LevelS& lv, const StepArgs& a) {
@@ -78,12 +79,15 @@ __device__ __forceinline__ void init_levels(LevelS& lv, const StepArgs& a) {
     lv.hsize[threadIdx.x] = g.hashmap_size;
     lv.off[threadIdx.x] = g.offset;
     lv.dense[threadIdx.x] = g.dense;
+    lv.hmask[threadIdx.x] = (g.hashmap_size & (g.hashmap_size - 1)) == 0 ? g.hashmap_size - 1 : 0u;
   }
 }
 
-__device__ __forceinline__ uint32_t corner_idx(uint32_t dense, uint32_t r1, uint32_t hsize, uint32_t x, uint32_t y, uint32_t z) {
+__device__ __forceinline__ uint32_t corner_idx(uint32_t dense, uint32_t r1, uint32_t hsize, uint32_t hmask, uint32_t x, uint32_t y,
+                                              uint32_t z) {
   if (dense) return x + y * r1 + z * r1 * r1;                    // < hsize by construction (gridencoder.cu:70-73)
-  return ((x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u)) % hsize;  // gridencoder.cu:78-82
+  const uint32_t h = (x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u);   // gridencoder.cu:78-82
+  return hmask ? (h & hmask) : (h % hsize);                      // `% 2^k` without the integer-division sequence
 }
 
 template <bool HALF> struct TableT;
@@ -158,7 +162,7 @@ template <bool HALF, bool WANT_J>
 __device__ __forceinline__ void gather_level(const void* table, const LevelS& lv, int l, const float u[3], float enc[2],
                                              float J[3][2]) {
   const float scale = lv.scale[l];
-  const uint32_t r1 = lv.res1[l], hs = lv.hsize[l], off = lv.off[l], dense = lv.dense[l];
+  const uint32_t r1 = lv.res1[l], hs = lv.hsize[l], off = lv.off[l], dense = lv.dense[l], hm = lv.hmask[l];
   float fr[3];
   uint32_t pg[3];
 #pragma unroll
@@ -171,7 +175,7 @@ __device__ __forceinline__ void gather_level(const void* table, const LevelS& lv
   float2 f[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const uint32_t idx = corner_idx(dense, r1, hs, pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1));
+    const uint32_t idx = corner_idx(dense, r1, hs, hm, pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1));
     f[c] = TableT<HALF>::load(table, off + idx);
   }
   const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
@@ -209,7 +213,7 @@ __device__ __forceinline__ void gather_level(const void* table, const LevelS& lv
 // fp16 atomics) — one vectorised reduction per corner.
 __device__ __forceinline__ void scatter_level(float* grad_table, const LevelS& lv, int l, const float u[3], float g0, float g1) {
   const float scale = lv.scale[l];
-  const uint32_t r1 = lv.res1[l], hs = lv.hsize[l], off = lv.off[l], dense = lv.dense[l];
+  const uint32_t r1 = lv.res1[l], hs = lv.hsize[l], off = lv.off[l], dense = lv.dense[l], hm = lv.hmask[l];
   float fr[3];
   uint32_t pg[3];
 #pragma unroll
@@ -222,7 +226,7 @@ __device__ __forceinline__ void scatter_level(float* grad_table, const LevelS& l
   const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const uint32_t idx = corner_idx(dense, r1, hs, pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1));
+    const uint32_t idx = corner_idx(dense, r1, hs, hm, pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1));
     const float w = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
     red_add_v2(grad_table + ((size_t)(off + idx)) * 2, w * g0, w * g1);
   }

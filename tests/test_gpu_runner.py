@@ -131,3 +131,48 @@ def test_render_contract():
     assert rgb.shape == (128, 3) and extras['raw'].shape == (128, 128, 4) and extras['z_vals'].shape == (128, 128)
     assert extras['valid_samples'].dtype == torch.bool
     assert float(r.adam_segs['table']['grad'].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('amp', [False, True])
+def test_training_trajectory_matches_oracle(amp):
+    """same init, same batches, same jitter -> the loss trajectory and the optimised parameters of the CUDA path
+    follow the CPU oracle (torch autograd + the oracle's Adam) over 25 optimizer steps."""
+    r, seq = _runner(amp, n_frames=4, N=192)
+    steps = 25
+    enc = r.models['embed_fn']
+    P = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in r.models['model'].state_dict().items()}
+    P['embeddings'] = enc.embeddings.detach().cpu().clone().requires_grad_(True)
+    P['offsets'] = enc.offsets.cpu().numpy(); P['S'] = float(np.log2(enc.per_level_scale)); P['H'] = 16
+    P['pose_data'] = r.models['pose_array'].data.detach().cpu().clone().requires_grad_(True)
+    P['feature_data'] = None
+    leaves = [P['embeddings']] + [P[k] for k in P if 'net' in k] + [P['pose_data']]
+    state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in leaves]
+    c2w, occ = r.c2w_array.cpu(), r.octree_m.occ.cpu().numpy()
+    gen = torch.Generator().manual_seed(5)
+    got, want = [], []
+    lr = 0.01
+    for it in range(steps):
+        batch = next(r.data_loader)
+        t_rand = torch.rand(batch.shape[0], 128, generator=gen)
+        b = r.train_loop(batch, t_rand=t_rand.cuda())
+        got.append(r.get_metrics())
+        zv = b['z_vals'].cpu()
+        out = O.forward_step(P, batch.cpu(), c2w, occ, r.cfg, half=amp, z_vals=zv)
+        for p in leaves:
+            p.grad = None
+        out['loss'].backward()
+        with torch.no_grad():
+            for p, (m, v) in zip(leaves, state):
+                O.adam_update(p, p.grad, m, v, it + 1, lr)
+        if it % 10 == 0 and it > 0:                        # schedule_lr (nerf_runner.py:762-763,579-583), applies from the next step
+            lr = O.lr_at(r.cfg, 0.01, it)
+        want.append({k: float(out[k].detach()) for k in ('loss', 'rgb_loss', 'fs_loss', 'sdf_loss')})
+        r.global_step += 1
+    tol = 0.08 if amp else 0.02
+    for it in range(steps):
+        for k in ('loss', 'rgb_loss', 'sdf_loss'):
+            assert abs(got[it][k] - want[it][k]) <= tol * max(abs(want[it][k]), 1e-3), (it, k, got[it][k], want[it][k])
+    assert want[-1]['sdf_loss'] < 0.8 * want[0]['sdf_loss']
+    rel = lambda a, w: np.abs(a - w).max() / max(np.abs(w).max(), 1e-30)
+    assert rel(r.models['model'].state_dict()['color_net.4.weight'].cpu().numpy(), P['color_net.4.weight'].detach().numpy()) < (0.15 if amp else 0.05)
+    assert rel(r.models['pose_array'].data.detach().cpu().numpy(), P['pose_data'].detach().numpy()) < (0.25 if amp else 0.1)
