@@ -44,7 +44,8 @@ struct Tiling { int NW, Sp, R, n_groups, blocks; };
 static bool amp_tiling(const NofStep* p, int sms, Tiling* t) {
   const int S = p->S;
   int T;
-  if (S <= 128) T = 128; else if (S <= 192) T = 192; else if (S <= 256) T = 256; else if (S <= 320) T = 320; else return false;
+  // 656 B of shared memory per point + 25 KB of weights: 256 points (193 KB) is the largest tile that fits 227 KB
+  if (S <= 128) T = 128; else if (S <= 192) T = 192; else if (S <= 256) T = 256; else return false;
   int Sp = T, R = 1;
   if (S <= 32) { Sp = 32; R = 4; } else if (S <= 64) { Sp = 64; R = 2; }
   t->NW = T / 32; t->Sp = Sp; t->R = R;
@@ -143,7 +144,7 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
   a.inv_NS3 = a.inv_NS / 3.0f;
   Tiling t;
   if (p->amp) {
-    NOF_REQUIRE(amp_tiling(p, sms, &t), "nof_step_fused(amp): S=%d > 320 samples per ray not supported", p->S);
+    NOF_REQUIRE(amp_tiling(p, sms, &t), "nof_step_fused(amp): S=%d > 256 samples per ray not supported by the AMP tile (use amp: false)", p->S);
     a.R = t.R; a.Sp = t.Sp; a.n_groups = t.n_groups;
     NOF_REQUIRE(step_amp_smem(t.NW * 32, a.KE) <= (size_t)smem_max, "nof_step_fused(amp): needs %zu B shared memory, device allows %d",
                 step_amp_smem(t.NW * 32, a.KE), smem_max);

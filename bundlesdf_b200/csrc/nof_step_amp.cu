@@ -5,16 +5,19 @@
 // vector reductions (red.global.add.v2.f32) for the grid gradient. Weights and biases are staged into shared
 // memory once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier).
 //
+// Tile = PT points = whole rays; the CTA runs 2*PT threads (two threads per point):
+//   * gather / scatter: the two threads of a point split the L levels (half each) -> twice the loads in flight per point
+//     and half the dependent round trips per thread;
+//   * MLP: warp w owns rows [16w, 16w+16) (one m16 tile) for forward and dgrad, all warps cooperate on wgrad;
+//   * 16 resident warps per SM (2 CTAs x 8 warps at PT=128) instead of 8: the kernel is latency-bound (ncu: issue
+//     utilisation 22 %, long-scoreboard stalls on the gather), see profiles/README.md.
+//
 // Replaces, for one batch: run_network + raw2outputs + loss assembly + loss.backward() of the reference
 // (nerf_runner.py:1083-1088,1227-1304,1132-1169,679-758; grid.py:34-99; gridencoder.cu:107-365).
 #include "nof_step_common.cuh"
 
 #ifndef NOF_GATHER_UNROLL
-#define NOF_GATHER_UNROLL 2      // levels of the multires gather in flight per thread (8 x 4-byte loads each); measured on
-                                 // B200 (profiles/README.md): 2 -> 334 us, 4 -> 398 us, 8 -> 443 us per C2 launch
-#endif
-#ifndef NOF_STAGGER_NS
-#define NOF_STAGGER_NS 0         // >0: odd CTAs start late so the two CTAs of an SM alternate gather / MLP phases
+#define NOF_GATHER_UNROLL 2      // levels of the multires gather in flight per thread (8 x 4-byte loads each)
 #endif
 
 namespace nof {
@@ -73,12 +76,11 @@ constexpr int LD32 = 40;   // stride of 32-wide
 constexpr int LD16 = 24;   // stride of 16-wide
 
 struct SmemPlan {
-  // offsets in bytes
-  int w1, w2, w3, w4, w5, bias, x0, x1, xc, x3, x4, d_o, out, rays, lv, bar, total;
+  int w1, w2, w3, w4, w5, bias, x0, x1, xc, x3, x4, d_o, out, rays, lv, bar, total;   // byte offsets
   int ldx0;                // stride (halfs) of X0 / W1 (KE + 8)
 };
 
-__host__ __device__ inline SmemPlan make_plan(int T, int KE) {
+__host__ __device__ inline SmemPlan make_plan(int PT, int KE) {
   SmemPlan s;
   s.ldx0 = KE + 8;
   int o = 0;
@@ -89,13 +91,13 @@ __host__ __device__ inline SmemPlan make_plan(int T, int KE) {
   s.w4 = take(64 * LD64 * 2);
   s.w5 = take(16 * LD64 * 2);
   s.bias = take(216 * 4);                    // b1 64, b2 16, b3 64, b4 64, b5 8
-  s.x0 = take(T * s.ldx0 * 2);
-  s.x1 = take(T * LD64 * 2);
-  s.xc = take(T * LD32 * 2);
-  s.x3 = take(T * LD64 * 2);
-  s.x4 = take(T * LD64 * 2);
-  s.d_o = take(T * LD16 * 2);                // dOut (phase 5), later dH2 (phase 2)
-  s.out = take(T * 4 * 4);                   // fp32 [T][4]
+  s.x0 = take(PT * s.ldx0 * 2);
+  s.x1 = take(PT * LD64 * 2);
+  s.xc = take(PT * LD32 * 2);
+  s.x3 = take(PT * LD64 * 2);
+  s.x4 = take(PT * LD64 * 2);
+  s.d_o = take(PT * LD16 * 2);               // dOut (phase 5), later dH2 (phase 2)
+  s.out = take(PT * 4 * 4);                  // fp32 [PT][4]
   s.rays = take(MAX_R * (int)sizeof(RayS));
   s.lv = take((int)sizeof(LevelS));
   s.bar = take(64);
@@ -104,64 +106,53 @@ __host__ __device__ inline SmemPlan make_plan(int T, int KE) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// warp-level GEMM pieces on the warp's own 32 rows (2 m-tiles)
+// warp-level GEMM pieces on the warp's own 16 rows (one m16 tile)
 // ------------------------------------------------------------------------------------------------
-// Y[32 x N] = A[32 x K] * W^T, W stored [N][K] (nn.Linear layout).  acc[mt][nt][4]
+// Y[16 x N] = A[16 x K] * W^T, W stored [N][K] (nn.Linear layout).  acc[nt][4]
 template <int K, int N>
-__device__ __forceinline__ void warp_fwd(const __half* A, int lda, const __half* W, int ldw, float (*acc)[N / 8][4], int lane) {
+__device__ __forceinline__ void warp_fwd(const __half* A, int lda, const __half* W, int ldw, float (*acc)[4], int lane) {
 #pragma unroll
   for (int ks = 0; ks < K / 16; ++ks) {
-    uint32_t a[2][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-      ldsm_x4(a[mt], A + (size_t)(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * lda + ks * 16 + (lane >> 4) * 8);
+    uint32_t a[4];
+    ldsm_x4(a, A + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * lda + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
     for (int np = 0; np < N / 16; ++np) {      // two n-tiles per ldmatrix.x4
       uint32_t b[4];
       ldsm_x4(b, W + (size_t)(np * 16 + (lane & 7) + (lane >> 4) * 8) * ldw + ks * 16 + ((lane >> 3) & 1) * 8);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        mma16816(acc[mt][np * 2], a[mt], b[0], b[1]);
-        mma16816(acc[mt][np * 2 + 1], a[mt], b[2], b[3]);
-      }
+      mma16816(acc[np * 2], a, b[0], b[1]);
+      mma16816(acc[np * 2 + 1], a, b[2], b[3]);
     }
-    if constexpr ((N / 8) % 2 == 1) {          // N == 8: single n-tile (x4 load reads 16 W rows; rows 8..15 exist, unused)
+    if constexpr ((N / 8) % 2 == 1) {          // N == 8: single n-tile (the x4 load reads 16 W rows; rows 8..15 exist, unused)
       uint32_t b[4];
       ldsm_x4(b, W + (size_t)((N / 16) * 16 + (lane & 7) + (lane >> 4) * 8) * ldw + ks * 16 + ((lane >> 3) & 1) * 8);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) mma16816(acc[mt][N / 8 - 1], a[mt], b[0], b[1]);
+      mma16816(acc[N / 8 - 1], a, b[0], b[1]);
     }
   }
 }
 
-// dX[32 x NI] = dY[32 x KO] * W, W stored [KO][NI] row-major (k = output index of the layer).
+// dX[16 x NI] = dY[16 x KO] * W, W stored [KO][NI] row-major (k = output index of the layer).
 template <int KO, int NI>
-__device__ __forceinline__ void warp_dgrad(const __half* dY, int ldy, const __half* W, int ldw, float (*acc)[NI / 8][4], int lane) {
+__device__ __forceinline__ void warp_dgrad(const __half* dY, int ldy, const __half* W, int ldw, float (*acc)[4], int lane) {
 #pragma unroll
   for (int ks = 0; ks < KO / 16; ++ks) {
-    uint32_t a[2][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-      ldsm_x4(a[mt], dY + (size_t)(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ldy + ks * 16 + (lane >> 4) * 8);
+    uint32_t a[4];
+    ldsm_x4(a, dY + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * ldy + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
     for (int np = 0; np < NI / 16; ++np) {
       uint32_t b[4];
       ldsm_x4_t(b, W + (size_t)(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ldw + np * 16 + (lane >> 4) * 8);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        mma16816(acc[mt][np * 2], a[mt], b[0], b[1]);
-        mma16816(acc[mt][np * 2 + 1], a[mt], b[2], b[3]);
-      }
+      mma16816(acc[np * 2], a, b[0], b[1]);
+      mma16816(acc[np * 2 + 1], a, b[2], b[3]);
     }
   }
 }
 
-// One wgrad unit: dW[strip*16 .. +16][nt0*8 .. +NTU*8] += dY^T X over all T rows of the CTA; bias via a ones B-operand.
+// One wgrad unit: dW[strip*16 .. +16][nt0*8 .. +NTU*8] += dY^T X over all PT rows of the CTA; bias via a ones B-operand.
 template <int NTU>
-__device__ __forceinline__ void wgrad_unit(const __half* dY, int ldy, const __half* X, int ldx, int T, int strip, int nt0,
+__device__ __forceinline__ void wgrad_unit(const __half* dY, int ldy, const __half* X, int ldx, int PT, int strip, int nt0,
                                            float acc[4][4], float* bias2, bool do_bias, int lane) {
   const uint32_t ones = 0x3C003C00u;
-  for (int ks = 0; ks < T / 16; ++ks) {
+  for (int ks = 0; ks < PT / 16; ++ks) {
     uint32_t a[4];
     ldsm_x4_t(a, dY + (size_t)(ks * 16 + (lane & 7) + (lane >> 4) * 8) * ldy + strip * 16 + ((lane >> 3) & 1) * 8);
 #pragma unroll
@@ -180,8 +171,8 @@ __device__ __forceinline__ void wgrad_unit(const __half* dY, int ldy, const __ha
   }
 }
 
-// wgrad unit list: (layer, strip, n-tile group). Unit u -> warp u % NW, slot u / NW.
-//   L1: 4 strips x (KE/8 n-tiles, in groups of NTU1)   L2: 1 strip x 8 nt -> 2 groups of 4
+// wgrad unit list: (layer, strip, n-tile group). Unit u -> warp u % NWARP, slot u / NWARP.
+//   L1: 4 strips x (KE/8 n-tiles, in groups of <=4)   L2: 1 strip x 8 nt -> 2 groups of 4
 //   L3: 4 strips x 4 nt                               L4: 4 strips x 8 nt -> 8 units     L5: 1 strip x 8 nt -> 2 units
 struct UnitMap {
   int l1, l2, l3, l4, l5, total;   // first unit id of each layer
@@ -198,23 +189,63 @@ __host__ __device__ constexpr UnitMap unit_map(int KE) {
 }
 constexpr int MAX_UNITS = 20;
 
-template <int NW>
+template <int NWARP>
 struct WgradAcc {
-  static constexpr int SLOTS = (MAX_UNITS + NW - 1) / NW;
+  static constexpr int SLOTS = (MAX_UNITS + NWARP - 1) / NWARP;
   float w[SLOTS][4][4];
   float b[SLOTS][2];
 };
 
+// epilogue helpers for one m16 tile ----------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void init_bias(float (*acc)[4], const float* bias, int t4) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    acc[nt][0] = bias[nt * 8 + 2 * t4]; acc[nt][1] = bias[nt * 8 + 2 * t4 + 1];
+    acc[nt][2] = acc[nt][0];            acc[nt][3] = acc[nt][1];
+  }
+}
+template <int NT>
+__device__ __forceinline__ void zero_acc(float (*acc)[4]) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+}
+// ReLU + fp16 store of a 16 x 64 tile
+__device__ __forceinline__ void store_relu64(__half* Y, int row0, const float (*acc)[4], int g8, int t4) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    __half* y = Y + (size_t)(row0 + g8) * LD64 + nt * 8 + 2 * t4;
+    *reinterpret_cast<uint32_t*>(y) = pack_h2(fmaxf(acc[nt][0], 0.f), fmaxf(acc[nt][1], 0.f));
+    *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(fmaxf(acc[nt][2], 0.f), fmaxf(acc[nt][3], 0.f));
+  }
+}
+// dY = dX * relu'(X) written in place over X (16 x 64 tile); returns true if an fp16 conversion overflowed
+__device__ __forceinline__ bool store_masked64(__half* X, int row0, const float (*acc)[4], int g8, int t4) {
+  bool ovf = false;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    __half* y = X + (size_t)(row0 + g8) * LD64 + nt * 8 + 2 * t4;
+    const __half2 m0 = *reinterpret_cast<__half2*>(y), m1 = *reinterpret_cast<__half2*>(y + 8 * LD64);
+    const float v0 = __low2float(m0) > 0.f ? acc[nt][0] : 0.f, v1 = __high2float(m0) > 0.f ? acc[nt][1] : 0.f;
+    const float v2 = __low2float(m1) > 0.f ? acc[nt][2] : 0.f, v3 = __high2float(m1) > 0.f ? acc[nt][3] : 0.f;
+    ovf |= !(fabsf(v0) <= 65504.f) || !(fabsf(v1) <= 65504.f) || !(fabsf(v2) <= 65504.f) || !(fabsf(v3) <= 65504.f);
+    *reinterpret_cast<uint32_t*>(y) = pack_h2(v0, v1);
+    *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(v2, v3);
+  }
+  return ovf;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int NW, int KE_>
-__global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(const StepArgs a) {
-  constexpr int T = NW * 32;
+template <int PT, int KE_>
+__global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(const StepArgs a) {
+  constexpr int NT = 2 * PT;                 // threads
+  constexpr int NWARP = NT / 32;
   constexpr int KE = KE_;
   constexpr int LDX0 = KE + 8;
   extern __shared__ __align__(128) unsigned char smem[];
-  const SmemPlan sp = make_plan(T, KE);
+  const SmemPlan sp = make_plan(PT, KE);
   __half* sW1 = reinterpret_cast<__half*>(smem + sp.w1);
   __half* sW2 = reinterpret_cast<__half*>(smem + sp.w2);
   __half* sW3 = reinterpret_cast<__half*>(smem + sp.w3);
@@ -252,29 +283,29 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(co
   }
   init_levels(lv, a);
   // zero the weight tiles (padding rows / columns must be exact zeros)
-  for (int i = tid; i < (sp.bias - sp.w1) / 4; i += T) reinterpret_cast<uint32_t*>(smem + sp.w1)[i] = 0u;
+  for (int i = tid; i < (sp.bias - sp.w1) / 4; i += NT) reinterpret_cast<uint32_t*>(smem + sp.w1)[i] = 0u;
   __syncthreads();
   mbar_wait(bar, 0);
   {
     const float* P = sStage;
-    for (int i = tid; i < 64 * E; i += T) sW1[(i / E) * LDX0 + (i % E)] = __float2half_rn(P[a.po[0] + i]);
-    for (int i = tid; i < 16 * 64; i += T) sW2[(i / 64) * LD64 + (i % 64)] = __float2half_rn(P[a.po[2] + i]);
+    for (int i = tid; i < 64 * E; i += NT) sW1[(i / E) * LDX0 + (i % E)] = __float2half_rn(P[a.po[0] + i]);
+    for (int i = tid; i < 16 * 64; i += NT) sW2[(i / 64) * LD64 + (i % 64)] = __float2half_rn(P[a.po[2] + i]);
     const int K3 = V + 15;
-    for (int i = tid; i < 64 * K3; i += T) sW3[(i / K3) * LD32 + (i % K3)] = __float2half_rn(P[a.po[4] + i]);
-    for (int i = tid; i < 64 * 64; i += T) sW4[(i / 64) * LD64 + (i % 64)] = __float2half_rn(P[a.po[6] + i]);
-    for (int i = tid; i < 3 * 64; i += T) sW5[(i / 64) * LD64 + (i % 64)] = __float2half_rn(P[a.po[8] + i]);
+    for (int i = tid; i < 64 * K3; i += NT) sW3[(i / K3) * LD32 + (i % K3)] = __float2half_rn(P[a.po[4] + i]);
+    for (int i = tid; i < 64 * 64; i += NT) sW4[(i / 64) * LD64 + (i % 64)] = __float2half_rn(P[a.po[6] + i]);
+    for (int i = tid; i < 3 * 64; i += NT) sW5[(i / 64) * LD64 + (i % 64)] = __float2half_rn(P[a.po[8] + i]);
     // biases: autocast rounds them to fp16 as well (F.linear casts all three operands)
-    for (int i = tid; i < 64; i += T) sB[i] = __half2float(__float2half_rn(P[a.po[1] + i]));
-    for (int i = tid; i < 16; i += T) sB[64 + i] = __half2float(__float2half_rn(P[a.po[3] + i]));
-    for (int i = tid; i < 64; i += T) sB[80 + i] = __half2float(__float2half_rn(P[a.po[5] + i]));
-    for (int i = tid; i < 64; i += T) sB[144 + i] = __half2float(__float2half_rn(P[a.po[7] + i]));
-    for (int i = tid; i < 8; i += T) sB[208 + i] = (i < 3) ? __half2float(__float2half_rn(P[a.po[9] + i])) : 0.f;
+    for (int i = tid; i < 64; i += NT) sB[i] = __half2float(__float2half_rn(P[a.po[1] + i]));
+    for (int i = tid; i < 16; i += NT) sB[64 + i] = __half2float(__float2half_rn(P[a.po[3] + i]));
+    for (int i = tid; i < 64; i += NT) sB[80 + i] = __half2float(__float2half_rn(P[a.po[5] + i]));
+    for (int i = tid; i < 64; i += NT) sB[144 + i] = __half2float(__float2half_rn(P[a.po[7] + i]));
+    for (int i = tid; i < 8; i += NT) sB[208 + i] = (i < 3) ? __half2float(__float2half_rn(P[a.po[9] + i])) : 0.f;
   }
   __syncthreads();
 
-  WgradAcc<NW> wg;
+  WgradAcc<NWARP> wg;
 #pragma unroll
-  for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
+  for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -286,13 +317,17 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(co
   bool overflow = false;
 
   const int Sp = a.Sp, R = a.R, S = a.p.S;
-  const int rl = tid / Sp, sidx = tid - rl * Sp;
-  __half2* Jslot = reinterpret_cast<__half2*>(a.p.workspace) + (size_t)blockIdx.x * (MAX_L * 3) * T;
+  // point owned by this thread in the per-point phases: both halves of the CTA see the same points
+  const int half = tid / PT;                 // 0: levels [0, LH) ; 1: levels [LH, L)
+  const int pt = tid - half * PT;
+  const int rl = pt / Sp, sidx = pt - rl * Sp;
+  const int LH = (L + 1) >> 1;
+  const int l_beg = half ? LH : 0, l_end = half ? L : LH;
+  const bool owner = half == 0;              // the thread that does the once-per-point work (compositing, seeds)
+  __half2* Jslot = reinterpret_cast<__half2*>(a.p.workspace) + (size_t)blockIdx.x * (MAX_L * 3) * PT;
   const int g8 = lane >> 2, t4 = lane & 3;
+  const int row0 = warp * 16;                // MLP rows of this warp
 
-#if NOF_STAGGER_NS > 0
-  if (blockIdx.x >= gridDim.x / 2) __nanosleep(NOF_STAGGER_NS);
-#endif
   for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
     // ============ 1. ray setup
     if (tid < R) setup_ray(sRay[tid], a, grp * R + tid);
@@ -306,7 +341,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(co
 #pragma unroll
     for (int d = 0; d < 3; ++d) u[d] = (x[d] + 1.0f) * 0.5f;                                        // grid.py:160
     const float w_raw = active ? raw_weight(a, z, rs.depth) : 0.f;
-    {
+    if (owner) {                                            // warp-uniform (PT is a multiple of 32)
       const float ws = warp_sum(w_raw);
       const unsigned anyv = __ballot_sync(0xffffffffu, valid);
       if (lane == 0) {
@@ -314,140 +349,90 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(co
         if (anyv) atomicOr(&sRay[rl].anyvalid, 1);
       }
     }
-    // ============ 2. colour-net input row (views part; geo filled by L2) and the multires gather
+    // ============ 2. colour-net input row (views part; geo filled by L2) and this thread's half of the multires gather
     {
-      __half* xc = XC + (size_t)tid * LD32;
+      if (!owner) {
+        __half* xc = XC + (size_t)pt * LD32;
 #pragma unroll 4
-      for (int j = 0; j < KC; ++j) xc[j] = __float2half_rn(j < V ? rs.views[j] : 0.f);
-      __half* x0 = X0 + (size_t)tid * LDX0;
+        for (int j = 0; j < KC; ++j) xc[j] = __float2half_rn(j < V ? rs.views[j] : 0.f);
+      }
+      __half* x0 = X0 + (size_t)pt * LDX0;
       if (valid) {
 #pragma unroll kGatherUnroll
-        for (int l = 0; l < L; ++l) {
+        for (int l = l_beg; l < l_end; ++l) {
           float enc[2], J[3][2];
           if (a.p.need_pose_grad) {
             gather_level<true, true>(a.p.table_f16, lv, l, u, enc, J);
 #pragma unroll
-            for (int d = 0; d < 3; ++d) Jslot[(size_t)(l * 3 + d) * T + tid] = __floats2half2_rn(J[d][0], J[d][1]);
+            for (int d = 0; d < 3; ++d) Jslot[(size_t)(l * 3 + d) * PT + pt] = __floats2half2_rn(J[d][0], J[d][1]);
           } else {
             gather_level<true, false>(a.p.table_f16, lv, l, u, enc, J);
           }
           *reinterpret_cast<__half2*>(x0 + 2 * l) = __floats2half2_rn(enc[0], enc[1]);
         }
-        for (int j = E; j < KE; ++j) x0[j] = __float2half_rn(0.f);
+        if (owner) for (int j = E; j < KE; ++j) x0[j] = __float2half_rn(0.f);
       } else {
-        for (int j = 0; j < KE; j += 2) *reinterpret_cast<uint32_t*>(x0 + j) = 0u;   // nerf_runner.py:1247: zeros for invalid
+        for (int j = 2 * l_beg; j < 2 * l_end; j += 2) *reinterpret_cast<uint32_t*>(x0 + j) = 0u;   // nerf_runner.py:1247: zeros for invalid
+        if (owner) for (int j = E; j < KE; ++j) x0[j] = __float2half_rn(0.f);
       }
     }
-    __syncwarp();
-    // ============ 3. MLP forward on the warp's own 32 rows
-    const int row0 = warp * 32;
+    __syncthreads();                                        // (A) rows are produced by two different warps
+    // ============ 3. MLP forward on the warp's own 16 rows
     {
-      float acc[2][8][4];
+      float acc[8][4];
       // ---- L1: E -> 64, ReLU
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          acc[mt][nt][0] = sB[nt * 8 + 2 * t4]; acc[mt][nt][1] = sB[nt * 8 + 2 * t4 + 1];
-          acc[mt][nt][2] = acc[mt][nt][0];      acc[mt][nt][3] = acc[mt][nt][1];
-        }
+      init_bias<8>(acc, sB, t4);
       warp_fwd<KE, 64>(X0 + (size_t)row0 * LDX0, LDX0, sW1, LDX0, acc, lane);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          __half* y = X1 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
-          *reinterpret_cast<uint32_t*>(y) = pack_h2(fmaxf(acc[mt][nt][0], 0.f), fmaxf(acc[mt][nt][1], 0.f));
-          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(fmaxf(acc[mt][nt][2], 0.f), fmaxf(acc[mt][nt][3], 0.f));
-        }
+      store_relu64(X1, row0, acc, g8, t4);
       __syncwarp();
       // ---- L2: 64 -> 16 (sdf | geo 15), no activation
-      float acc2[2][2][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          acc2[mt][nt][0] = sB[64 + nt * 8 + 2 * t4]; acc2[mt][nt][1] = sB[64 + nt * 8 + 2 * t4 + 1];
-          acc2[mt][nt][2] = acc2[mt][nt][0];          acc2[mt][nt][3] = acc2[mt][nt][1];
-        }
+      float acc2[2][4];
+      init_bias<2>(acc2, sB + 64, t4);
       warp_fwd<64, 16>(X1 + (size_t)row0 * LD64, LD64, sW2, LD64, acc2, lane);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r = row0 + mt * 16 + g8 + h * 8;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int col = nt * 8 + 2 * t4 + c;
-              const __half hv = __float2half_rn(acc2[mt][nt][h * 2 + c]);
-              if (col == 0) sOut[r * 4 + 3] = __half2float(hv);            // sdf (nerf_helpers.py:312)
-              else XC[(size_t)r * LD32 + V + col - 1] = hv;                 // geo feature -> colour-net input (:316)
-            }
-          }
-      __syncwarp();
-      // ---- L3: (V+15 padded 32) -> 64, ReLU
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          acc[mt][nt][0] = sB[80 + nt * 8 + 2 * t4]; acc[mt][nt][1] = sB[80 + nt * 8 + 2 * t4 + 1];
-          acc[mt][nt][2] = acc[mt][nt][0];           acc[mt][nt][3] = acc[mt][nt][1];
-        }
-      warp_fwd<KC, 64>(XC + (size_t)row0 * LD32, LD32, sW3, LD32, acc, lane);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          __half* y = X3 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
-          *reinterpret_cast<uint32_t*>(y) = pack_h2(fmaxf(acc[mt][nt][0], 0.f), fmaxf(acc[mt][nt][1], 0.f));
-          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(fmaxf(acc[mt][nt][2], 0.f), fmaxf(acc[mt][nt][3], 0.f));
-        }
-      __syncwarp();
-      // ---- L4: 64 -> 64, ReLU
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          acc[mt][nt][0] = sB[144 + nt * 8 + 2 * t4]; acc[mt][nt][1] = sB[144 + nt * 8 + 2 * t4 + 1];
-          acc[mt][nt][2] = acc[mt][nt][0];            acc[mt][nt][3] = acc[mt][nt][1];
-        }
-      warp_fwd<64, 64>(X3 + (size_t)row0 * LD64, LD64, sW4, LD64, acc, lane);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          __half* y = X4 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
-          *reinterpret_cast<uint32_t*>(y) = pack_h2(fmaxf(acc[mt][nt][0], 0.f), fmaxf(acc[mt][nt][1], 0.f));
-          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(fmaxf(acc[mt][nt][2], 0.f), fmaxf(acc[mt][nt][3], 0.f));
-        }
-      __syncwarp();
-      // ---- L5: 64 -> 3 (padded 8)
-      float acc5[2][1][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        acc5[mt][0][0] = sB[208 + 2 * t4]; acc5[mt][0][1] = sB[208 + 2 * t4 + 1];
-        acc5[mt][0][2] = acc5[mt][0][0];   acc5[mt][0][3] = acc5[mt][0][1];
-      }
-      warp_fwd<64, 8>(X4 + (size_t)row0 * LD64, LD64, sW5, LD64, acc5, lane);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h) {
+          const int r = row0 + g8 + h * 8;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const int col = 2 * t4 + c;
-            if (col < 3) sOut[(row0 + mt * 16 + g8 + h * 8) * 4 + col] = __half2float(__float2half_rn(acc5[mt][0][h * 2 + c]));
+            const int col = nt * 8 + 2 * t4 + c;
+            const __half hv = __float2half_rn(acc2[nt][h * 2 + c]);
+            if (col == 0) sOut[r * 4 + 3] = __half2float(hv);              // sdf (nerf_helpers.py:312)
+            else XC[(size_t)r * LD32 + V + col - 1] = hv;                   // geo feature -> colour-net input (:316)
           }
+        }
+      __syncwarp();
+      // ---- L3: (V+15 padded 32) -> 64, ReLU
+      init_bias<8>(acc, sB + 80, t4);
+      warp_fwd<KC, 64>(XC + (size_t)row0 * LD32, LD32, sW3, LD32, acc, lane);
+      store_relu64(X3, row0, acc, g8, t4);
+      __syncwarp();
+      // ---- L4: 64 -> 64, ReLU
+      init_bias<8>(acc, sB + 144, t4);
+      warp_fwd<64, 64>(X3 + (size_t)row0 * LD64, LD64, sW4, LD64, acc, lane);
+      store_relu64(X4, row0, acc, g8, t4);
+      __syncwarp();
+      // ---- L5: 64 -> 3 (padded 8)
+      float acc5[1][4];
+      init_bias<1>(acc5, sB + 208, t4);
+      warp_fwd<64, 8>(X4 + (size_t)row0 * LD64, LD64, sW5, LD64, acc5, lane);
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = 2 * t4 + c;
+          if (col < 3) sOut[(row0 + g8 + h * 8) * 4 + col] = __half2float(__float2half_rn(acc5[0][h * 2 + c]));
+        }
     }
     __syncthreads();                                        // (B) sumw / anyvalid complete, sOut rows visible
-    // ============ 4. compositing (nerf_runner.py:1163-1167)
-    float out4[4];
+    // ============ 4. compositing (nerf_runner.py:1163-1167) — once per point (owner threads)
+    float out4[4] = {0.f, 0.f, 0.f, 0.f};
+    float w = 0.f;
+    if (owner) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) out4[c] = sOut[tid * 4 + c];
-    const float w = valid ? w_raw / (rs.sumw + 1e-10f) : 0.f;
-    {
+      for (int c = 0; c < 4; ++c) out4[c] = sOut[pt * 4 + c];
+      w = valid ? w_raw / (rs.sumw + 1e-10f) : 0.f;
       float pr[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) pr[c] = warp_sum(w * sigmoidf_(out4[c]));
@@ -458,33 +443,34 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(co
     }
     __syncthreads();                                        // (C) rgb_map complete
     // ============ 5. loss seeds
-    const float ray_w = rs.ray_w_base * (rs.anyvalid ? 1.f : 0.f);
-    float d_out[4];
-    loss_seeds(a, rs, out4, z, w, valid, active ? ray_w : 0.f, d_out, loss_acc);
-    if (!active) { d_out[0] = d_out[1] = d_out[2] = d_out[3] = 0.f; }
-    if (valid) n_valid_s += 1.f;
-    if (sidx == 0 && rs.active) {
-      float e = 0.f;
+    float dsdf_s = 0.f;
+    if (owner) {
+      const float ray_w = rs.ray_w_base * (rs.anyvalid ? 1.f : 0.f);
+      float d_out[4];
+      loss_seeds(a, rs, out4, z, w, valid, active ? ray_w : 0.f, d_out, loss_acc);
+      if (!active) { d_out[0] = d_out[1] = d_out[2] = d_out[3] = 0.f; }
+      if (valid) n_valid_s += 1.f;
+      if (sidx == 0 && rs.active) {
+        float e = 0.f;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { const float dd = rs.rgb[c] - rs.gt[c]; e += dd * dd; }
-      loss_acc[1] += a.p.rgb_weight * e * ray_w * a.inv_N3;                     // nerf_runner.py:700-701
-      if (rs.anyvalid && rs.ray_w_base != 0.f) n_valid_r += 1.f;
-      if (a.p.rgb_map) {
+        for (int c = 0; c < 3; ++c) { const float dd = rs.rgb[c] - rs.gt[c]; e += dd * dd; }
+        loss_acc[1] += a.p.rgb_weight * e * ray_w * a.inv_N3;                     // nerf_runner.py:700-701
+        if (rs.anyvalid && rs.ray_w_base != 0.f) n_valid_r += 1.f;
+        if (a.p.rgb_map) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) a.p.rgb_map[(size_t)rs.ray * 3 + c] = rs.rgb[c];
+          for (int c = 0; c < 3; ++c) a.p.rgb_map[(size_t)rs.ray * 3 + c] = rs.rgb[c];
+        }
       }
-    }
-    if (active) {
-      const size_t pi = (size_t)rs.ray * S + sidx;
-      if (a.p.raw) *reinterpret_cast<float4*>(a.p.raw + pi * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
-      if (a.p.valid_samples) a.p.valid_samples[pi] = valid ? 1 : 0;
-      if (a.p.weights) a.p.weights[pi] = w;
-    }
-    float dsdf_s = d_out[3] * scale_ls;
-    {
-      float s0 = d_out[0] * scale_ls, s1 = d_out[1] * scale_ls, s2 = d_out[2] * scale_ls;
+      if (active) {
+        const size_t pi = (size_t)rs.ray * S + sidx;
+        if (a.p.raw) *reinterpret_cast<float4*>(a.p.raw + pi * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+        if (a.p.valid_samples) a.p.valid_samples[pi] = valid ? 1 : 0;
+        if (a.p.weights) a.p.weights[pi] = w;
+      }
+      dsdf_s = d_out[3] * scale_ls;
+      const float s0 = d_out[0] * scale_ls, s1 = d_out[1] * scale_ls, s2 = d_out[2] * scale_ls;
       overflow |= !(fabsf(s0) <= 65504.f) || !(fabsf(s1) <= 65504.f) || !(fabsf(s2) <= 65504.f) || !(fabsf(dsdf_s) <= 65504.f);
-      __half* dr = DO + (size_t)tid * LD16;
+      __half* dr = DO + (size_t)pt * LD16;
       *reinterpret_cast<uint32_t*>(dr) = pack_h2(s0, s1);
       *reinterpret_cast<uint32_t*>(dr + 2) = pack_h2(s2, 0.f);
 #pragma unroll
@@ -495,134 +481,88 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(co
     // ============ 6. backward through the MLP
     // ---- layer 5: wgrad (all rows) + dgrad (own rows) -> dY4 = dX4 * relu'(X4), in place
 #pragma unroll
-    for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
-      const int uid = s * NW + warp;
-      if (uid >= um.l5 && uid < um.total) wgrad_unit<4>(DO, LD16, X4, LD64, T, 0, (uid - um.l5) * 4, wg.w[s], wg.b[s], uid == um.l5, lane);
+    for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
+      const int uid = s * NWARP + warp;
+      if (uid >= um.l5 && uid < um.total) wgrad_unit<4>(DO, LD16, X4, LD64, PT, 0, (uid - um.l5) * 4, wg.w[s], wg.b[s], uid == um.l5, lane);
     }
     {
-      float acc[2][8][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+      float acc[8][4];
+      zero_acc<8>(acc);
       warp_dgrad<16, 64>(DO + (size_t)row0 * LD16, LD16, sW5, LD64, acc, lane);
       __syncthreads();                                      // every warp finished reading X4 (wgrad5)
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          __half* y = X4 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
-          const __half2 m0 = *reinterpret_cast<__half2*>(y), m1 = *reinterpret_cast<__half2*>(y + 8 * LD64);
-          const float v0 = __low2float(m0) > 0.f ? acc[mt][nt][0] : 0.f, v1 = __high2float(m0) > 0.f ? acc[mt][nt][1] : 0.f;
-          const float v2 = __low2float(m1) > 0.f ? acc[mt][nt][2] : 0.f, v3 = __high2float(m1) > 0.f ? acc[mt][nt][3] : 0.f;
-          overflow |= !(fabsf(v0) <= 65504.f) || !(fabsf(v1) <= 65504.f) || !(fabsf(v2) <= 65504.f) || !(fabsf(v3) <= 65504.f);
-          *reinterpret_cast<uint32_t*>(y) = pack_h2(v0, v1);
-          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(v2, v3);
-        }
+      overflow |= store_masked64(X4, row0, acc, g8, t4);
     }
     __syncthreads();                                        // dY4 visible
     // ---- layer 4
 #pragma unroll
-    for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
-      const int uid = s * NW + warp;
+    for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
+      const int uid = s * NWARP + warp;
       if (uid >= um.l4 && uid < um.l5) {
         const int k = uid - um.l4;
-        wgrad_unit<4>(X4, LD64, X3, LD64, T, k >> 1, (k & 1) * 4, wg.w[s], wg.b[s], (k & 1) == 0, lane);
+        wgrad_unit<4>(X4, LD64, X3, LD64, PT, k >> 1, (k & 1) * 4, wg.w[s], wg.b[s], (k & 1) == 0, lane);
       }
     }
     {
-      float acc[2][8][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+      float acc[8][4];
+      zero_acc<8>(acc);
       warp_dgrad<64, 64>(X4 + (size_t)row0 * LD64, LD64, sW4, LD64, acc, lane);
       __syncthreads();                                      // wgrad4 finished reading X3
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          __half* y = X3 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
-          const __half2 m0 = *reinterpret_cast<__half2*>(y), m1 = *reinterpret_cast<__half2*>(y + 8 * LD64);
-          const float v0 = __low2float(m0) > 0.f ? acc[mt][nt][0] : 0.f, v1 = __high2float(m0) > 0.f ? acc[mt][nt][1] : 0.f;
-          const float v2 = __low2float(m1) > 0.f ? acc[mt][nt][2] : 0.f, v3 = __high2float(m1) > 0.f ? acc[mt][nt][3] : 0.f;
-          overflow |= !(fabsf(v0) <= 65504.f) || !(fabsf(v1) <= 65504.f) || !(fabsf(v2) <= 65504.f) || !(fabsf(v3) <= 65504.f);
-          *reinterpret_cast<uint32_t*>(y) = pack_h2(v0, v1);
-          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(v2, v3);
-        }
+      overflow |= store_masked64(X3, row0, acc, g8, t4);
     }
     __syncthreads();                                        // dY3 visible
     // ---- layer 3: wgrad (dY3^T XC), dgrad -> [dviews | dgeo]
 #pragma unroll
-    for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
-      const int uid = s * NW + warp;
-      if (uid >= um.l3 && uid < um.l4) wgrad_unit<4>(X3, LD64, XC, LD32, T, uid - um.l3, 0, wg.w[s], wg.b[s], true, lane);
+    for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
+      const int uid = s * NWARP + warp;
+      if (uid >= um.l3 && uid < um.l4) wgrad_unit<4>(X3, LD64, XC, LD32, PT, uid - um.l3, 0, wg.w[s], wg.b[s], true, lane);
     }
     {
-      float acc[2][4][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+      float acc[4][4];
+      zero_acc<4>(acc);
       warp_dgrad<64, KC>(X3 + (size_t)row0 * LD64, LD64, sW3, LD32, acc, lane);
-      // dviews: sum over the 32 rows of this warp (all samples of one ray) — warp-level reduction, then one shared
+      // dviews: sum over the 16 rows of this warp (samples of one ray) — warp-level reduction, then one shared
       // atomic per column per warp.
+      const int ray_of_rows = row0 / Sp;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int col = nt * 8 + 2 * t4 + c;
-          float v = acc[0][nt][c] + acc[0][nt][2 + c] + acc[1][nt][c] + acc[1][nt][2 + c];
+          float v = acc[nt][c] + acc[nt][2 + c];
           v += __shfl_xor_sync(0xffffffffu, v, 4);
           v += __shfl_xor_sync(0xffffffffu, v, 8);
           v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (g8 == 0 && col < V && v != 0.f) atomicAdd(&sRay[rl].dviews[col], v);
+          if (g8 == 0 && col < V && v != 0.f) atomicAdd(&sRay[ray_of_rows].dviews[col], v);
         }
       // dH2 = [dsdf | dgeo] -> DO buffer (dOut is dead: wgrad5/dgrad5 completed before the barriers above)
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int col = nt * 8 + 2 * t4 + c;
-              if (col >= V && col < V + 15) {
-                const float v = acc[mt][nt][h * 2 + c];
-                overflow |= !(fabsf(v) <= 65504.f);
-                DO[(size_t)(row0 + mt * 16 + g8 + h * 8) * LD16 + 1 + (col - V)] = __float2half_rn(v);
-              }
+          for (int c = 0; c < 2; ++c) {
+            const int col = nt * 8 + 2 * t4 + c;
+            if (col >= V && col < V + 15) {
+              const float v = acc[nt][h * 2 + c];
+              overflow |= !(fabsf(v) <= 65504.f);
+              DO[(size_t)(row0 + g8 + h * 8) * LD16 + 1 + (col - V)] = __float2half_rn(v);
             }
-      DO[(size_t)tid * LD16] = __float2half_rn(dsdf_s);
+          }
+      if (owner) DO[(size_t)pt * LD16] = __float2half_rn(dsdf_s);
     }
     __syncthreads();                                        // dH2 visible
     // ---- layer 2
 #pragma unroll
-    for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
-      const int uid = s * NW + warp;
-      if (uid >= um.l2 && uid < um.l3) wgrad_unit<4>(DO, LD16, X1, LD64, T, 0, (uid - um.l2) * 4, wg.w[s], wg.b[s], uid == um.l2, lane);
+    for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
+      const int uid = s * NWARP + warp;
+      if (uid >= um.l2 && uid < um.l3) wgrad_unit<4>(DO, LD16, X1, LD64, PT, 0, (uid - um.l2) * 4, wg.w[s], wg.b[s], uid == um.l2, lane);
     }
     {
-      float acc[2][8][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+      float acc[8][4];
+      zero_acc<8>(acc);
       warp_dgrad<16, 64>(DO + (size_t)row0 * LD16, LD16, sW2, LD64, acc, lane);
       __syncthreads();                                      // wgrad2 finished reading X1
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          __half* y = X1 + (size_t)(row0 + mt * 16 + g8) * LD64 + nt * 8 + 2 * t4;
-          const __half2 m0 = *reinterpret_cast<__half2*>(y), m1 = *reinterpret_cast<__half2*>(y + 8 * LD64);
-          const float v0 = __low2float(m0) > 0.f ? acc[mt][nt][0] : 0.f, v1 = __high2float(m0) > 0.f ? acc[mt][nt][1] : 0.f;
-          const float v2 = __low2float(m1) > 0.f ? acc[mt][nt][2] : 0.f, v3 = __high2float(m1) > 0.f ? acc[mt][nt][3] : 0.f;
-          overflow |= !(fabsf(v0) <= 65504.f) || !(fabsf(v1) <= 65504.f) || !(fabsf(v2) <= 65504.f) || !(fabsf(v3) <= 65504.f);
-          *reinterpret_cast<uint32_t*>(y) = pack_h2(v0, v1);
-          *reinterpret_cast<uint32_t*>(y + 8 * LD64) = pack_h2(v2, v3);
-        }
+      overflow |= store_masked64(X1, row0, acc, g8, t4);
     }
     __syncthreads();                                        // dY1 visible
     // ---- layer 1: wgrad (dY1^T X0), dgrad -> dEnc (fp32, scaled) into the X3 region (dead)
@@ -631,43 +571,38 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(co
       constexpr int NTU1 = NT1 < 4 ? NT1 : 4;
       constexpr int G1 = (NT1 + 3) / 4;                     // n-tile groups per strip
 #pragma unroll
-      for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
-        const int uid = s * NW + warp;
+      for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
+        const int uid = s * NWARP + warp;
         if (uid >= um.l1 && uid < um.l2) {
           const int k = uid - um.l1;
-          wgrad_unit<NTU1>(X1, LD64, X0, LDX0, T, k / G1, (k % G1) * 4, wg.w[s], wg.b[s], (k % G1) == 0, lane);
+          wgrad_unit<NTU1>(X1, LD64, X0, LDX0, PT, k / G1, (k % G1) * 4, wg.w[s], wg.b[s], (k % G1) == 0, lane);
         }
       }
-      float acc[2][NT1][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < NT1; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+      float acc[NT1][4];
+      zero_acc<NT1>(acc);
       warp_dgrad<64, KE>(X1 + (size_t)row0 * LD64, LD64, sW1, LDX0, acc, lane);
-      float* dE = reinterpret_cast<float*>(X3);             // [T][36] fp32 (144-byte rows)
+      float* dE = reinterpret_cast<float*>(X3);             // [PT][36] fp32 (144-byte rows)
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < NT1; ++nt) {
-          float* y = dE + (size_t)(row0 + mt * 16 + g8) * 36 + nt * 8 + 2 * t4;
-          *reinterpret_cast<float2*>(y) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
-          *reinterpret_cast<float2*>(y + 8 * 36) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
-        }
+      for (int nt = 0; nt < NT1; ++nt) {
+        float* y = dE + (size_t)(row0 + g8) * 36 + nt * 8 + 2 * t4;
+        *reinterpret_cast<float2*>(y) = make_float2(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<float2*>(y + 8 * 36) = make_float2(acc[nt][2], acc[nt][3]);
+      }
     }
-    __syncwarp();
-    // ============ 7. grid-gradient scatter + pose Jacobian (path A: positions) for this thread's point
+    __syncthreads();                                        // dEnc rows visible to the two threads of each point
+    // ============ 7. grid-gradient scatter + pose Jacobian (path A: positions) for this thread's half of the levels
     {
-      const float* dE = reinterpret_cast<const float*>(X3) + (size_t)tid * 36;
+      const float* dE = reinterpret_cast<const float*>(X3) + (size_t)pt * 36;
       float gx[3] = {0.f, 0.f, 0.f};
       if (valid) {
 #pragma unroll 2
-        for (int l = 0; l < L; ++l) {
+        for (int l = l_beg; l < l_end; ++l) {
           const float2 g = *reinterpret_cast<const float2*>(dE + 2 * l);
           if (g.x != 0.f || g.y != 0.f) scatter_level(a.p.grad_table, lv, l, u, g.x, g.y);
           if (a.p.need_pose_grad) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-              const float2 j = __half22float2(Jslot[(size_t)(l * 3 + d) * T + tid]);
+              const float2 j = __half22float2(Jslot[(size_t)(l * 3 + d) * PT + pt]);
               gx[d] = fmaf(g.x, j.x, fmaf(g.y, j.y, gx[d]));
             }
           }
@@ -720,8 +655,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(co
     float* G = a.p.grad_mlp;
     const int K3 = V + 15;
 #pragma unroll
-    for (int s = 0; s < WgradAcc<NW>::SLOTS; ++s) {
-      const int uid = s * NW + warp;
+    for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
+      const int uid = s * NWARP + warp;
       if (uid >= um.total) continue;
       int strip, nt0, ncols, nrows, wofs, bofs;
       if (uid < um.l2) { constexpr int G1 = (KE / 8 + 3) / 4; const int k = uid - um.l1; strip = k / G1; nt0 = (k % G1) * 4; ncols = E; nrows = 64; wofs = a.po[0]; bofs = a.po[1]; }
@@ -762,31 +697,31 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 2 : 1) step_amp_kernel(co
 }
 
 // ------------------------------------------------------------------------------------------------
-size_t step_amp_smem(int T, int KE) { return (size_t)make_plan(T, KE).total; }
+size_t step_amp_smem(int PT, int KE) { return (size_t)make_plan(PT, KE).total; }
 
-template <int NW, int KE>
+template <int PT, int KE>
 static int launch_amp(const StepArgs& a, int blocks, cudaStream_t st) {
-  const size_t smem = step_amp_smem(NW * 32, KE);
+  const size_t smem = step_amp_smem(PT, KE);
   static bool once = false;
   if (!once) {
-    cudaFuncSetAttribute(step_amp_kernel<NW, KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(step_amp_kernel<PT, KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     once = true;
   }
-  step_amp_kernel<NW, KE><<<blocks, NW * 32, smem, st>>>(a);
+  step_amp_kernel<PT, KE><<<blocks, 2 * PT, smem, st>>>(a);
   return check_launch("step_amp_kernel");
 }
 
+// NW = points per tile / 32 (4, 6 or 8)
 int step_amp_dispatch(const StepArgs& a, int NW, int blocks, cudaStream_t st) {
-#define NOF_AMP_CASE(nw)                                                     \
-  case nw:                                                                   \
-    if (a.KE == 32) return launch_amp<nw, 32>(a, blocks, st);                \
-    if (a.KE == 16) return launch_amp<nw, 16>(a, blocks, st);                \
+#define NOF_AMP_CASE(nw)                                                          \
+  case nw:                                                                        \
+    if (a.KE == 32) return launch_amp<nw * 32, 32>(a, blocks, st);                \
+    if (a.KE == 16) return launch_amp<nw * 32, 16>(a, blocks, st);                \
     break;
   switch (NW) {
     NOF_AMP_CASE(4)
     NOF_AMP_CASE(6)
     NOF_AMP_CASE(8)
-    NOF_AMP_CASE(10)
     default: break;
   }
 #undef NOF_AMP_CASE

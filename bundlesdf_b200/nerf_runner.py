@@ -649,6 +649,9 @@ class NerfRunner:
             self.adam_step_count.fill_(int(torch.as_tensor(st['step']).item()))
         for g, sg in zip(self.optimizer.param_groups, saved['param_groups']):
             g['lr'] = sg['lr']
+        self.lr_dev.copy_(torch.tensor([g['lr'] for g in self.optimizer.param_groups], dtype=torch.float32))
+        if 'amp_scaler' in ckpt and self.amp_scaler.enabled:
+            self.amp_scaler.state.copy_(torch.tensor([float(ckpt['amp_scaler']['scale']), float(ckpt['amp_scaler']['_growth_tracker'])]))
         del live
         self.global_step = int(ckpt.get('global_step', 0))
         self._step_buf = None

@@ -173,6 +173,8 @@ def test_training_trajectory_matches_oracle(amp):
         for k in ('loss', 'rgb_loss', 'sdf_loss'):
             assert abs(got[it][k] - want[it][k]) <= tol * max(abs(want[it][k]), 1e-3), (it, k, got[it][k], want[it][k])
     assert want[-1]['sdf_loss'] < 0.8 * want[0]['sdf_loss']
-    rel = lambda a, w: np.abs(a - w).max() / max(np.abs(w).max(), 1e-30)
-    assert rel(r.models['model'].state_dict()['color_net.4.weight'].cpu().numpy(), P['color_net.4.weight'].detach().numpy()) < (0.15 if amp else 0.05)
-    assert rel(r.models['pose_array'].data.detach().cpu().numpy(), P['pose_data'].detach().numpy()) < (0.25 if amp else 0.1)
+    # Adam (eps=1e-15) turns a noise-sized gradient into a full +-lr step, so single entries may differ by several lr after
+    # 25 steps; compare in the L2 sense.
+    rel = lambda a, w: np.linalg.norm(a - w) / max(np.linalg.norm(w), 1e-30)
+    assert rel(r.models['model'].state_dict()['color_net.4.weight'].cpu().numpy(), P['color_net.4.weight'].detach().numpy()) < (0.1 if amp else 0.03)
+    assert rel(r.models['pose_array'].data.detach().cpu().numpy(), P['pose_data'].detach().numpy()) < (0.2 if amp else 0.1)
