@@ -10,7 +10,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--config', default='C2')
 ap.add_argument('--frames', type=int, default=24)
 ap.add_argument('--reps', type=int, default=50)
+ap.add_argument('--fp32', action='store_true', help='cfg amp: false (fp32 policy kernel)')
 args = ap.parse_args()
+if args.fp32:
+    _mk = bench.make_cfg
+    bench.make_cfg = lambda c: dict(_mk(c), amp=False)
 c = dict(bench.CONFIGS[args.config]); c['frames'] = min(c['frames'], args.frames)
 torch.cuda.set_device(0)
 runner, seq = bench.build_runner(c, 0, torch.device('cuda', 0), eager=True)
