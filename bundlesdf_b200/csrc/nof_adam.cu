@@ -57,8 +57,13 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a, co
   __shared__ float s_bc[3];
   if (threadIdx.x == 0) {
     const int step = (step_ptr ? __ldg(step_ptr) : 0) + 1;  // this update's 1-based step
-    s_bc[0] = (float)(1.0 / (1.0 - pow((double)a.beta1, (double)step)));
-    s_bc[1] = (float)sqrt(1.0 - pow((double)a.beta2, (double)step));
+    if (step_ptr && __ldg(step_ptr + 3) == step) {          // bias corrections cached by the previous adam_finish_kernel
+      s_bc[0] = __int_as_float(__ldg(step_ptr + 1));
+      s_bc[1] = __int_as_float(__ldg(step_ptr + 2));
+    } else {                                                // first step / externally modified counter: FP64 pow here
+      s_bc[0] = (float)(1.0 / (1.0 - pow((double)a.beta1, (double)step)));
+      s_bc[1] = (float)sqrt(1.0 - pow((double)a.beta2, (double)step));
+    }
     s_bc[2] = scale_state ? 1.0f / __ldg(scale_state) : 1.0f;
   }
   __syncthreads();
@@ -108,10 +113,17 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a, co
 }
 
 // GradScaler.update() (growth_factor 2, backoff 0.5, growth_interval 2000) + step counter + RNG tick + flag reset.
-__global__ void adam_finish_kernel(int32_t* step_ptr, float* scale_state, int32_t* found_inf, unsigned long long* tick) {
+__global__ void adam_finish_kernel(int32_t* step_ptr, float* scale_state, int32_t* found_inf, unsigned long long* tick, float beta1,
+                                   float beta2) {
   if (tick) *tick += 1ull;
   const bool inf = found_inf && (*found_inf != 0);
   if (!inf && step_ptr) *step_ptr += 1;
+  if (step_ptr) {                                           // cache the NEXT update's bias corrections (torch computes them in fp64)
+    const int next = *step_ptr + 1;
+    step_ptr[1] = __float_as_int((float)(1.0 / (1.0 - pow((double)beta1, (double)next))));
+    step_ptr[2] = __float_as_int((float)sqrt(1.0 - pow((double)beta2, (double)next)));
+    step_ptr[3] = next;
+  }
   if (scale_state) {
     if (inf) {
       scale_state[0] *= 0.5f;
@@ -159,6 +171,6 @@ extern "C" int nof_adam_step(const NofAdamSeg* segs, int n_segs, float beta1, fl
     int rc = check_launch("adam_kernel");
     if (rc) return rc;
   }
-  adam_finish_kernel<<<1, 1, 0, st>>>(step, scale_state, found_inf, reinterpret_cast<unsigned long long*>(tick));
+  adam_finish_kernel<<<1, 1, 0, st>>>(step, scale_state, found_inf, reinterpret_cast<unsigned long long*>(tick), beta1, beta2);
   return check_launch("adam_finish_kernel");
 }

@@ -203,7 +203,8 @@ class NerfRunner:
         self.param_groups_init = copy.deepcopy(self.optimizer.param_groups)
         dev = self.device
         z = lambda t: torch.zeros_like(t)
-        self.adam_step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._adam_step_buf = torch.zeros(4, dtype=torch.int32, device=dev)   # [0] step count, [1..3] library scratch (nof.h)
+        self.adam_step_count = self._adam_step_buf[:1]
         # device-resident step state so that a captured CUDA graph of the step never needs new launch arguments:
         # learning rates (one per param group) and the RNG tick the sampler adds to its Philox offset
         self.lr_dev = torch.tensor([g['lr'] for g in groups], dtype=torch.float32, device=dev)
@@ -455,7 +456,7 @@ class NerfRunner:
     def _optimizer_step(self):
         groups = self.optimizer.param_groups
         segs = [dict(s, lr=groups[s['group']]['lr']) for s in self.adam_segs.values()]
-        ops.adam_step(segs, 0.9, 0.999, 1e-15, self.adam_step_count, self.amp_scaler.state if self.amp_scaler.enabled else None,
+        ops.adam_step(segs, 0.9, 0.999, 1e-15, self._adam_step_buf, self.amp_scaler.state if self.amp_scaler.enabled else None,
                       self.amp_scaler.found_inf, tick=self.tick)
 
     def _graph_usable(self, t_rand):
@@ -646,7 +647,8 @@ class NerfRunner:
             mine = self.optimizer.state[p]
             mine['exp_avg'].copy_(st['exp_avg'])
             mine['exp_avg_sq'].copy_(st['exp_avg_sq'])
-            self.adam_step_count.fill_(int(torch.as_tensor(st['step']).item()))
+            self._adam_step_buf.zero_()                        # also invalidates the cached bias corrections
+            self.adam_step_count.fill_(int(torch.as_tensor(st['step']).reshape(-1)[0].item()))
         for g, sg in zip(self.optimizer.param_groups, saved['param_groups']):
             g['lr'] = sg['lr']
         self.lr_dev.copy_(torch.tensor([g['lr'] for g in self.optimizer.param_groups], dtype=torch.float32))
