@@ -147,20 +147,21 @@ __device__ __forceinline__ void warp_dgrad(const __half* dY, int ldy, const __ha
   }
 }
 
-// One wgrad unit: dW[strip*16 .. +16][nt0*8 .. +NTU*8] += dY^T X over all PT rows of the CTA; bias via a ones B-operand.
+// One wgrad item: dW[strip*16 .. +16][nt0*8 .. +NTU*8] += dY^T X over all PT rows of the CTA; bias via a ones B-operand.
+// (For odd NTU the x4 load of the last pair also reads the 8 columns after the tile: they are inside the row padding.)
 template <int NTU>
-__device__ __forceinline__ void wgrad_unit(const __half* dY, int ldy, const __half* X, int ldx, int PT, int strip, int nt0,
-                                           float acc[4][4], float* bias2, bool do_bias, int lane) {
+__device__ __forceinline__ void wgrad_item(const __half* dY, int ldy, const __half* X, int ldx, int PT, int strip, int nt0,
+                                           float (*acc)[4], float* bias2, bool do_bias, int lane) {
   const uint32_t ones = 0x3C003C00u;
   for (int ks = 0; ks < PT / 16; ++ks) {
     uint32_t a[4];
     ldsm_x4_t(a, dY + (size_t)(ks * 16 + (lane & 7) + (lane >> 4) * 8) * ldy + strip * 16 + ((lane >> 3) & 1) * 8);
 #pragma unroll
-    for (int np = 0; np < NTU / 2; ++np) {
+    for (int np = 0; np < (NTU + 1) / 2; ++np) {
       uint32_t b[4];
       ldsm_x4_t(b, X + (size_t)(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ldx + (nt0 + np * 2) * 8 + (lane >> 4) * 8);
       mma16816(acc[np * 2], a, b[0], b[1]);
-      mma16816(acc[np * 2 + 1], a, b[2], b[3]);
+      if (np * 2 + 1 < NTU) mma16816(acc[np * 2 + 1], a, b[2], b[3]);
     }
     if (do_bias) {
       float t[4] = {0.f, 0.f, 0.f, 0.f};
@@ -171,30 +172,42 @@ __device__ __forceinline__ void wgrad_unit(const __half* dY, int ldy, const __ha
   }
 }
 
-// wgrad unit list: (layer, strip, n-tile group). Unit u -> warp u % NWARP, slot u / NWARP.
-//   L1: 4 strips x (KE/8 n-tiles, in groups of <=4)   L2: 1 strip x 8 nt -> 2 groups of 4
-//   L3: 4 strips x 4 nt                               L4: 4 strips x 8 nt -> 8 units     L5: 1 strip x 8 nt -> 2 units
-struct UnitMap {
-  int l1, l2, l3, l4, l5, total;   // first unit id of each layer
+// Even split of one layer's weight gradient (NS strips of 16 output rows x NTL n-tiles of 8 input columns) over the warps of
+// the CTA: every warp owns at most ONE item (strip, CNT consecutive n-tiles) per layer, so each wgrad phase keeps all warps
+// busy for the same time (the first version gave whole layers to 2-4 warps and the rest waited at the barrier: ncu showed
+// 21 % barrier stalls). CNT = smallest divisor of NTL that is >= NS*NTL/NWARP; accumulators stay in registers for the
+// whole kernel: (CNT1 + 1 + 2 + 4 + 1) * 4 floats.
+template <int NS, int NTL, int NWARP>
+struct WSplit {
+  static constexpr int ideal = (NS * NTL + NWARP - 1) / NWARP;
+  static constexpr int CNT = ideal <= 1 ? 1 : (ideal <= 2 ? (NTL % 2 == 0 ? 2 : NTL) : (NTL % 4 == 0 ? 4 : NTL));
+  static constexpr int GROUPS = NTL / CNT;
+  static constexpr int ITEMS = NS * GROUPS;
+  static_assert(CNT <= 4 && NTL % CNT == 0, "wgrad split");
 };
-__host__ __device__ constexpr UnitMap unit_map(int KE) {
-  UnitMap m{};
-  m.l1 = 0;
-  m.l2 = m.l1 + 4 * ((KE / 8 + 3) / 4);
-  m.l3 = m.l2 + 2;
-  m.l4 = m.l3 + 4;
-  m.l5 = m.l4 + 8;
-  m.total = m.l5 + 2;
-  return m;
-}
-constexpr int MAX_UNITS = 20;
 
-template <int NWARP>
-struct WgradAcc {
-  static constexpr int SLOTS = (MAX_UNITS + NWARP - 1) / NWARP;
-  float w[SLOTS][4][4];
-  float b[SLOTS][2];
-};
+// registers -> global (fp32 atomics) for one item
+template <int CNT>
+__device__ __forceinline__ void flush_item(float* G, int wofs, int bofs, int ncols, int nrows, int strip, int nt0, const float (*acc)[4],
+                                           const float* bias2, bool has_bias, int g8, int t4) {
+#pragma unroll
+  for (int nt = 0; nt < CNT; ++nt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int o = strip * 16 + g8 + h * 8, i = (nt0 + nt) * 8 + 2 * t4 + c;
+        const float v = acc[nt][h * 2 + c];
+        if (o < nrows && i < ncols && v != 0.f) red_add(G + wofs + (size_t)o * ncols + i, v);
+      }
+  if (has_bias && t4 == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int o = strip * 16 + g8 + h * 8;
+      if (o < nrows && bias2[h] != 0.f) red_add(G + bofs + o, bias2[h]);
+    }
+  }
+}
 
 // epilogue helpers for one m16 tile ----------------------------------------------------------------
 template <int NT>
@@ -267,7 +280,6 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int E = a.E, V = a.V, L = a.p.L;
   const float scale_ls = a.p.loss_scale ? *a.p.loss_scale : 1.0f;
-  constexpr UnitMap um = unit_map(KE);
 
   // ---- stage parameters: TMA bulk copy of the packed fp32 block into smem, then convert to padded fp16 tiles
   const int n_par = a.po[9] + 3;
@@ -303,15 +315,15 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
   }
   __syncthreads();
 
-  WgradAcc<NWARP> wg;
-#pragma unroll
-  for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) wg.w[s][i][j] = 0.f;
-    wg.b[s][0] = wg.b[s][1] = 0.f;
-  }
+  // weight-gradient accumulators: one item per layer per warp, kept in registers across all tiles of this CTA
+  using S1 = WSplit<4, KE / 8, NWARP>;
+  using S2 = WSplit<1, 8, NWARP>;
+  using S3 = WSplit<4, KC / 8, NWARP>;
+  using S4 = WSplit<4, 8, NWARP>;
+  using S5 = WSplit<1, 8, NWARP>;
+  float wg1[S1::CNT][4], wg2[S2::CNT][4], wg3[S3::CNT][4], wg4[S4::CNT][4], wg5[S5::CNT][4];
+  float wb1[2] = {0.f, 0.f}, wb2[2] = {0.f, 0.f}, wb3[2] = {0.f, 0.f}, wb4[2] = {0.f, 0.f}, wb5[2] = {0.f, 0.f};
+  zero_acc<S1::CNT>(wg1); zero_acc<S2::CNT>(wg2); zero_acc<S3::CNT>(wg3); zero_acc<S4::CNT>(wg4); zero_acc<S5::CNT>(wg5);
   float loss_acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   float n_valid_s = 0.f, n_valid_r = 0.f;
   bool overflow = false;
@@ -480,11 +492,8 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
 
     // ============ 6. backward through the MLP
     // ---- layer 5: wgrad (all rows) + dgrad (own rows) -> dY4 = dX4 * relu'(X4), in place
-#pragma unroll
-    for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
-      const int uid = s * NWARP + warp;
-      if (uid >= um.l5 && uid < um.total) wgrad_unit<4>(DO, LD16, X4, LD64, PT, 0, (uid - um.l5) * 4, wg.w[s], wg.b[s], uid == um.l5, lane);
-    }
+    if (warp < S5::ITEMS)
+      wgrad_item<S5::CNT>(DO, LD16, X4, LD64, PT, 0, (warp % S5::GROUPS) * S5::CNT, wg5, wb5, (warp % S5::GROUPS) == 0, lane);
     {
       float acc[8][4];
       zero_acc<8>(acc);
@@ -494,14 +503,8 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
     }
     __syncthreads();                                        // dY4 visible
     // ---- layer 4
-#pragma unroll
-    for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
-      const int uid = s * NWARP + warp;
-      if (uid >= um.l4 && uid < um.l5) {
-        const int k = uid - um.l4;
-        wgrad_unit<4>(X4, LD64, X3, LD64, PT, k >> 1, (k & 1) * 4, wg.w[s], wg.b[s], (k & 1) == 0, lane);
-      }
-    }
+    if (warp < S4::ITEMS)
+      wgrad_item<S4::CNT>(X4, LD64, X3, LD64, PT, warp / S4::GROUPS, (warp % S4::GROUPS) * S4::CNT, wg4, wb4, (warp % S4::GROUPS) == 0, lane);
     {
       float acc[8][4];
       zero_acc<8>(acc);
@@ -511,11 +514,8 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
     }
     __syncthreads();                                        // dY3 visible
     // ---- layer 3: wgrad (dY3^T XC), dgrad -> [dviews | dgeo]
-#pragma unroll
-    for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
-      const int uid = s * NWARP + warp;
-      if (uid >= um.l3 && uid < um.l4) wgrad_unit<4>(X3, LD64, XC, LD32, PT, uid - um.l3, 0, wg.w[s], wg.b[s], true, lane);
-    }
+    if (warp < S3::ITEMS)
+      wgrad_item<S3::CNT>(X3, LD64, XC, LD32, PT, warp / S3::GROUPS, (warp % S3::GROUPS) * S3::CNT, wg3, wb3, (warp % S3::GROUPS) == 0, lane);
     {
       float acc[4][4];
       zero_acc<4>(acc);
@@ -552,11 +552,8 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
     }
     __syncthreads();                                        // dH2 visible
     // ---- layer 2
-#pragma unroll
-    for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
-      const int uid = s * NWARP + warp;
-      if (uid >= um.l2 && uid < um.l3) wgrad_unit<4>(DO, LD16, X1, LD64, PT, 0, (uid - um.l2) * 4, wg.w[s], wg.b[s], uid == um.l2, lane);
-    }
+    if (warp < S2::ITEMS)
+      wgrad_item<S2::CNT>(DO, LD16, X1, LD64, PT, 0, (warp % S2::GROUPS) * S2::CNT, wg2, wb2, (warp % S2::GROUPS) == 0, lane);
     {
       float acc[8][4];
       zero_acc<8>(acc);
@@ -568,16 +565,8 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
     // ---- layer 1: wgrad (dY1^T X0), dgrad -> dEnc (fp32, scaled) into the X3 region (dead)
     {
       constexpr int NT1 = KE / 8;
-      constexpr int NTU1 = NT1 < 4 ? NT1 : 4;
-      constexpr int G1 = (NT1 + 3) / 4;                     // n-tile groups per strip
-#pragma unroll
-      for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
-        const int uid = s * NWARP + warp;
-        if (uid >= um.l1 && uid < um.l2) {
-          const int k = uid - um.l1;
-          wgrad_unit<NTU1>(X1, LD64, X0, LDX0, PT, k / G1, (k % G1) * 4, wg.w[s], wg.b[s], (k % G1) == 0, lane);
-        }
-      }
+      if (warp < S1::ITEMS)
+        wgrad_item<S1::CNT>(X1, LD64, X0, LDX0, PT, warp / S1::GROUPS, (warp % S1::GROUPS) * S1::CNT, wg1, wb1, (warp % S1::GROUPS) == 0, lane);
       float acc[NT1][4];
       zero_acc<NT1>(acc);
       warp_dgrad<64, KE>(X1 + (size_t)row0 * LD64, LD64, sW1, LDX0, acc, lane);
@@ -654,34 +643,16 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
   {
     float* G = a.p.grad_mlp;
     const int K3 = V + 15;
-#pragma unroll
-    for (int s = 0; s < WgradAcc<NWARP>::SLOTS; ++s) {
-      const int uid = s * NWARP + warp;
-      if (uid >= um.total) continue;
-      int strip, nt0, ncols, nrows, wofs, bofs;
-      if (uid < um.l2) { constexpr int G1 = (KE / 8 + 3) / 4; const int k = uid - um.l1; strip = k / G1; nt0 = (k % G1) * 4; ncols = E; nrows = 64; wofs = a.po[0]; bofs = a.po[1]; }
-      else if (uid < um.l3) { strip = 0; nt0 = (uid - um.l2) * 4; ncols = 64; nrows = 16; wofs = a.po[2]; bofs = a.po[3]; }
-      else if (uid < um.l4) { strip = uid - um.l3; nt0 = 0; ncols = K3; nrows = 64; wofs = a.po[4]; bofs = a.po[5]; }
-      else if (uid < um.l5) { const int k = uid - um.l4; strip = k >> 1; nt0 = (k & 1) * 4; ncols = 64; nrows = 64; wofs = a.po[6]; bofs = a.po[7]; }
-      else { strip = 0; nt0 = (uid - um.l5) * 4; ncols = 64; nrows = 3; wofs = a.po[8]; bofs = a.po[9]; }
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int o = strip * 16 + g8 + h * 8, i = (nt0 + nt) * 8 + 2 * t4 + c;
-            const float v = wg.w[s][nt][h * 2 + c];
-            if (o < nrows && i < ncols && v != 0.f) red_add(G + wofs + (size_t)o * ncols + i, v);
-          }
-      if (nt0 == 0 && t4 == 0) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int o = strip * 16 + g8 + h * 8;
-          if (o < nrows && wg.b[s][h] != 0.f) red_add(G + bofs + o, wg.b[s][h]);
-        }
-      }
-    }
+    if (warp < S1::ITEMS)
+      flush_item<S1::CNT>(G, a.po[0], a.po[1], E, 64, warp / S1::GROUPS, (warp % S1::GROUPS) * S1::CNT, wg1, wb1, (warp % S1::GROUPS) == 0, g8, t4);
+    if (warp < S2::ITEMS)
+      flush_item<S2::CNT>(G, a.po[2], a.po[3], 64, 16, 0, (warp % S2::GROUPS) * S2::CNT, wg2, wb2, (warp % S2::GROUPS) == 0, g8, t4);
+    if (warp < S3::ITEMS)
+      flush_item<S3::CNT>(G, a.po[4], a.po[5], K3, 64, warp / S3::GROUPS, (warp % S3::GROUPS) * S3::CNT, wg3, wb3, (warp % S3::GROUPS) == 0, g8, t4);
+    if (warp < S4::ITEMS)
+      flush_item<S4::CNT>(G, a.po[6], a.po[7], 64, 64, warp / S4::GROUPS, (warp % S4::GROUPS) * S4::CNT, wg4, wb4, (warp % S4::GROUPS) == 0, g8, t4);
+    if (warp < S5::ITEMS)
+      flush_item<S5::CNT>(G, a.po[8], a.po[9], 64, 3, 0, (warp % S5::GROUPS) * S5::CNT, wg5, wb5, (warp % S5::GROUPS) == 0, g8, t4);
   }
   {
     loss_acc[0] = loss_acc[1] + loss_acc[2] + loss_acc[3] + loss_acc[4];
