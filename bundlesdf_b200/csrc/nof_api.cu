@@ -30,6 +30,19 @@ size_t step_amp_smem(int T, int KE);
 size_t step_f32_smem(int E, int V, int grp_pts);
 int step_amp_dispatch(const StepArgs& a, int NW, int blocks, cudaStream_t st);
 int step_f32_dispatch(const StepArgs& a, int blocks, cudaStream_t st);
+size_t step_tc_smem(int KE);
+int step_tc_dispatch(const StepArgs& a, int blocks, cudaStream_t st);
+
+// The 128-point AMP tile has two implementations of the MLP GEMMs: tcgen05/TMEM (default) and mma.sync (NOF_AMP_IMPL=mma,
+// kept as the cross-check; larger tiles always use it).
+static bool amp_use_tcgen05() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NOF_AMP_IMPL");
+    v = (e && strcmp(e, "mma") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
 
 static void mlp_offsets(int E, int V, int32_t o[10], size_t* total) {
   const int sizes[10] = {64 * E, 64, 16 * 64, 16, 64 * (V + 15), 64, 64 * 64, 64, 3 * 64, 3};
@@ -146,6 +159,11 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
   if (p->amp) {
     NOF_REQUIRE(amp_tiling(p, sms, &t), "nof_step_fused(amp): S=%d > 256 samples per ray not supported by the AMP tile (use amp: false)", p->S);
     a.R = t.R; a.Sp = t.Sp; a.n_groups = t.n_groups;
+    if (t.NW == 4 && amp_use_tcgen05()) {
+      NOF_REQUIRE(step_tc_smem(a.KE) <= (size_t)smem_max, "nof_step_fused(amp, tcgen05): needs %zu B shared memory, device allows %d",
+                  step_tc_smem(a.KE), smem_max);
+      return step_tc_dispatch(a, t.blocks, as_stream(stream));
+    }
     NOF_REQUIRE(step_amp_smem(t.NW * 32, a.KE) <= (size_t)smem_max, "nof_step_fused(amp): needs %zu B shared memory, device allows %d",
                 step_amp_smem(t.NW * 32, a.KE), smem_max);
     return step_amp_dispatch(a, t.NW, t.blocks, as_stream(stream));

@@ -111,6 +111,9 @@ __host__ __device__ inline SmemPlan make_plan(int PT, int KE) {
 // Y[16 x N] = A[16 x K] * W^T, W stored [N][K] (nn.Linear layout).  acc[nt][4]
 template <int K, int N>
 __device__ __forceinline__ void warp_fwd(const __half* A, int lda, const __half* W, int ldw, float (*acc)[4], int lane) {
+#ifdef NOF_EXP_NO_MMA      // profiling experiment only: the kernel without its tensor-core work
+  return;
+#endif
 #pragma unroll
   for (int ks = 0; ks < K / 16; ++ks) {
     uint32_t a[4];
@@ -133,6 +136,9 @@ __device__ __forceinline__ void warp_fwd(const __half* A, int lda, const __half*
 // dX[16 x NI] = dY[16 x KO] * W, W stored [KO][NI] row-major (k = output index of the layer).
 template <int KO, int NI>
 __device__ __forceinline__ void warp_dgrad(const __half* dY, int ldy, const __half* W, int ldw, float (*acc)[4], int lane) {
+#ifdef NOF_EXP_NO_MMA
+  return;
+#endif
 #pragma unroll
   for (int ks = 0; ks < KO / 16; ++ks) {
     uint32_t a[4];
@@ -152,6 +158,9 @@ __device__ __forceinline__ void warp_dgrad(const __half* dY, int ldy, const __ha
 template <int NTU>
 __device__ __forceinline__ void wgrad_item(const __half* dY, int ldy, const __half* X, int ldx, int PT, int strip, int nt0,
                                            float (*acc)[4], float* bias2, bool do_bias, int lane) {
+#ifdef NOF_EXP_NO_MMA
+  return;
+#endif
   const uint32_t ones = 0x3C003C00u;
   for (int ks = 0; ks < PT / 16; ++ks) {
     uint32_t a[4];

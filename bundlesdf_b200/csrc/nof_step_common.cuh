@@ -176,7 +176,11 @@ __device__ __forceinline__ void gather_level(const void* table, const LevelS& lv
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const uint32_t idx = corner_idx(dense, r1, hs, hm, pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1));
+#ifdef NOF_EXP_NO_GATHER  // profiling experiment only: same index arithmetic, no table loads
+    f[c] = make_float2(__uint_as_float((off + idx) & 0x3fu) * 1e30f, 0.25f);
+#else
     f[c] = TableT<HALF>::load(table, off + idx);
+#endif
   }
   const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
   float e0 = 0.f, e1 = 0.f;
@@ -228,7 +232,11 @@ __device__ __forceinline__ void scatter_level(float* grad_table, const LevelS& l
   for (int c = 0; c < 8; ++c) {
     const uint32_t idx = corner_idx(dense, r1, hs, hm, pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1));
     const float w = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
+#ifdef NOF_EXP_NO_RED     // profiling experiment only (profiles/README.md): what the kernel costs without the reductions
+    if (w * g0 == 123456.f) red_add_v2(grad_table + ((size_t)(off + idx)) * 2, w * g0, w * g1);
+#else
     red_add_v2(grad_table + ((size_t)(off + idx)) * 2, w * g0, w * g1);
+#endif
   }
 }
 
