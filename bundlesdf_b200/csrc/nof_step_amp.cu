@@ -608,20 +608,25 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
       }
       if (a.p.need_pose_grad) {
         // dL/dx = 0.5 * dL/du ; dL/dR[i][j] += gx[i]*pc[j] ; dL/dt[i] += gx[i]   (x = R pc + t)
-        float gtf[12];
+        // x = R (dir z) + t  =>  dL/dR[i][j] = dir[j] * sum_p gi z ,  dL/dt[i] = sum_p gi   (gi = 0.5 gx[i]: u = (x+1)/2):
+        // six warp sums instead of twelve (all lanes of a warp belong to one ray).
+        float st[6];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const float gi = 0.5f * gx[i];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) gtf[i * 4 + j] = gi * pc[j];
-          gtf[i * 4 + 3] = gi;
+          st[i] = warp_sum(gi);
+          st[3 + i] = warp_sum(gi * z);
         }
-#pragma unroll
-        for (int i = 0; i < 12; ++i) gtf[i] = warp_sum(gtf[i]);
         if (lane == 0 && rs.active && rs.frame != 0) {
 #pragma unroll
-          for (int i = 0; i < 12; ++i)
-            if (gtf[i] != 0.f) red_add(a.p.grad_tf + (size_t)rs.frame * 12 + i, gtf[i]);
+          for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float v = st[3 + i] * rs.dir[j];
+              if (v != 0.f) red_add(a.p.grad_tf + (size_t)rs.frame * 12 + i * 4 + j, v);
+            }
+            if (st[i] != 0.f) red_add(a.p.grad_tf + (size_t)rs.frame * 12 + i * 4 + 3, st[i]);
+          }
         }
       }
     }

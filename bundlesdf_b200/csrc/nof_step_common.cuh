@@ -83,11 +83,33 @@ __device__ __forceinline__ void init_levels(LevelS& lv, const StepArgs& a) {
   }
 }
 
-__device__ __forceinline__ uint32_t corner_idx(uint32_t dense, uint32_t r1, uint32_t hsize, uint32_t hmask, uint32_t x, uint32_t y,
-                                              uint32_t z) {
-  if (dense) return x + y * r1 + z * r1 * r1;                    // < hsize by construction (gridencoder.cu:70-73)
-  const uint32_t h = (x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u);   // gridencoder.cu:78-82
-  return hmask ? (h & hmask) : (h % hsize);                      // `% 2^k` without the integer-division sequence
+// Table entries of the 8 corners of one cell (gridencoder.cu:62-84): corner c = (c&1, (c>>1)&1, (c>>2)&1). The level is
+// warp-uniform, so the dense / hashed split is a real branch; both forms are incremental (uint32 wrap-around arithmetic is
+// exact: (y+1)*p == y*p + p mod 2^32), ~20 integer instructions per cell instead of ~45.
+__device__ __forceinline__ void corner_indices(const LevelS& lv, int l, const uint32_t pg[3], uint32_t idx[8]) {
+  const uint32_t r1 = lv.res1[l];
+  if (lv.dense[l]) {                                              // x + y*r1 + z*r1^2, < hsize by construction (:70-73)
+    const uint32_t sz = r1 * r1;
+    const uint32_t b00 = pg[0] + pg[1] * r1 + pg[2] * sz, b10 = b00 + r1, b01 = b00 + sz, b11 = b10 + sz;
+    idx[0] = b00; idx[1] = b00 + 1u; idx[2] = b10; idx[3] = b10 + 1u;
+    idx[4] = b01; idx[5] = b01 + 1u; idx[6] = b11; idx[7] = b11 + 1u;
+  } else {                                                        // x ^ y*2654435761 ^ z*805459861 (:78-82)
+    const uint32_t hx0 = pg[0], hx1 = pg[0] + 1u;
+    const uint32_t hy0 = pg[1] * 2654435761u, hy1 = hy0 + 2654435761u;
+    const uint32_t hz0 = pg[2] * 805459861u, hz1 = hz0 + 805459861u;
+    const uint32_t a00 = hy0 ^ hz0, a10 = hy1 ^ hz0, a01 = hy0 ^ hz1, a11 = hy1 ^ hz1;
+    idx[0] = hx0 ^ a00; idx[1] = hx1 ^ a00; idx[2] = hx0 ^ a10; idx[3] = hx1 ^ a10;
+    idx[4] = hx0 ^ a01; idx[5] = hx1 ^ a01; idx[6] = hx0 ^ a11; idx[7] = hx1 ^ a11;
+    const uint32_t hm = lv.hmask[l];
+    if (hm) {                                                     // `% 2^k` without the integer-division sequence
+#pragma unroll
+      for (int c = 0; c < 8; ++c) idx[c] &= hm;
+    } else {
+      const uint32_t hs = lv.hsize[l];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) idx[c] %= hs;
+    }
+  }
 }
 
 template <bool HALF> struct TableT;
@@ -158,11 +180,13 @@ __device__ __forceinline__ void world_point(const RayS& rs, float z, float pc[3]
 }
 
 // One level of the multires gather for one point: enc (C=2) and, if WANT_J, J[d][c] = d enc/d u (gridencoder.cu:155-245).
+// Trilinear interpolation as nested lerps (x, then y, then z): the differences each lerp needs ARE the Jacobian terms, so
+// enc + J cost ~52 flops instead of ~104 for the weight-per-corner form (differs from it by fp32 rounding only).
 template <bool HALF, bool WANT_J>
 __device__ __forceinline__ void gather_level(const void* table, const LevelS& lv, int l, const float u[3], float enc[2],
                                              float J[3][2]) {
   const float scale = lv.scale[l];
-  const uint32_t r1 = lv.res1[l], hs = lv.hsize[l], off = lv.off[l], dense = lv.dense[l], hm = lv.hmask[l];
+  const uint32_t off = lv.off[l];
   float fr[3];
   uint32_t pg[3];
 #pragma unroll
@@ -172,44 +196,43 @@ __device__ __forceinline__ void gather_level(const void* table, const LevelS& lv
     pg[d] = (uint32_t)fl;
     fr[d] = p - fl;
   }
+  uint32_t idx[8];
+  corner_indices(lv, l, pg, idx);
   float2 f[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const uint32_t idx = corner_idx(dense, r1, hs, hm, pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1));
 #ifdef NOF_EXP_NO_GATHER  // profiling experiment only: same index arithmetic, no table loads
-    f[c] = make_float2(__uint_as_float((off + idx) & 0x3fu) * 1e30f, 0.25f);
+    f[c] = make_float2(__uint_as_float((off + idx[c]) & 0x3fu) * 1e30f, 0.25f);
 #else
-    f[c] = TableT<HALF>::load(table, off + idx);
+    f[c] = TableT<HALF>::load(table, off + idx[c]);
 #endif
   }
-  const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
-  float e0 = 0.f, e1 = 0.f;
+  // x: pairs (0,1) (2,3) (4,5) (6,7) -> lx[yz], dx[yz]
+  float2 dx[4], lx[4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float w = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
-    e0 = fmaf(w, f[c].x, e0);
-    e1 = fmaf(w, f[c].y, e1);
+  for (int k = 0; k < 4; ++k) {
+    dx[k] = make_float2(f[2 * k + 1].x - f[2 * k].x, f[2 * k + 1].y - f[2 * k].y);
+    lx[k] = make_float2(fmaf(fr[0], dx[k].x, f[2 * k].x), fmaf(fr[0], dx[k].y, f[2 * k].y));
   }
-  enc[0] = e0; enc[1] = e1;
+  // y: (lx[0],lx[1]) at z=0, (lx[2],lx[3]) at z=1
+  float2 dy[2], ly[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    dy[k] = make_float2(lx[2 * k + 1].x - lx[2 * k].x, lx[2 * k + 1].y - lx[2 * k].y);
+    ly[k] = make_float2(fmaf(fr[1], dy[k].x, lx[2 * k].x), fmaf(fr[1], dy[k].y, lx[2 * k].y));
+  }
+  const float2 dz = make_float2(ly[1].x - ly[0].x, ly[1].y - ly[0].y);
+  enc[0] = fmaf(fr[2], dz.x, ly[0].x);
+  enc[1] = fmaf(fr[2], dz.y, ly[0].y);
   if (WANT_J) {
-#pragma unroll
-    for (int gd = 0; gd < 3; ++gd) {
-      float j0 = 0.f, j1 = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        // the two other dims
-        const int d0 = (gd == 0) ? 1 : 0, d1 = (gd == 2) ? 1 : 2;
-        const int b0 = k & 1, b1 = (k >> 1) & 1;
-        const float w0 = (d0 == 0 ? wx[b0] : wy[b0]);
-        const float w1 = (d1 == 2 ? wz[b1] : wy[b1]);
-        const float w = scale * w0 * w1;
-        const int base = (b0 << d0) | (b1 << d1);
-        const float2 lo = f[base], hi = f[base | (1 << gd)];
-        j0 = fmaf(w, hi.x - lo.x, j0);
-        j1 = fmaf(w, hi.y - lo.y, j1);
-      }
-      J[gd][0] = j0; J[gd][1] = j1;
-    }
+    const float wy1 = fr[1], wy0 = 1.f - fr[1], wz1 = fr[2], wz0 = 1.f - fr[2];
+    const float w00 = wy0 * wz0, w10 = wy1 * wz0, w01 = wy0 * wz1, w11 = wy1 * wz1;      // [y][z] ; dx index k = y + 2 z
+    J[0][0] = scale * fmaf(w11, dx[3].x, fmaf(w01, dx[2].x, fmaf(w10, dx[1].x, w00 * dx[0].x)));
+    J[0][1] = scale * fmaf(w11, dx[3].y, fmaf(w01, dx[2].y, fmaf(w10, dx[1].y, w00 * dx[0].y)));
+    J[1][0] = scale * fmaf(wz1, dy[1].x, wz0 * dy[0].x);
+    J[1][1] = scale * fmaf(wz1, dy[1].y, wz0 * dy[0].y);
+    J[2][0] = scale * dz.x;
+    J[2][1] = scale * dz.y;
   }
 }
 
@@ -217,7 +240,7 @@ __device__ __forceinline__ void gather_level(const void* table, const LevelS& lv
 // fp16 atomics) — one vectorised reduction per corner.
 __device__ __forceinline__ void scatter_level(float* grad_table, const LevelS& lv, int l, const float u[3], float g0, float g1) {
   const float scale = lv.scale[l];
-  const uint32_t r1 = lv.res1[l], hs = lv.hsize[l], off = lv.off[l], dense = lv.dense[l], hm = lv.hmask[l];
+  const uint32_t off = lv.off[l];
   float fr[3];
   uint32_t pg[3];
 #pragma unroll
@@ -227,15 +250,16 @@ __device__ __forceinline__ void scatter_level(float* grad_table, const LevelS& l
     pg[d] = (uint32_t)fl;
     fr[d] = p - fl;
   }
+  uint32_t idx[8];
+  corner_indices(lv, l, pg, idx);
   const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const uint32_t idx = corner_idx(dense, r1, hs, hm, pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1));
     const float w = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
 #ifdef NOF_EXP_NO_RED     // profiling experiment only (profiles/README.md): what the kernel costs without the reductions
-    if (w * g0 == 123456.f) red_add_v2(grad_table + ((size_t)(off + idx)) * 2, w * g0, w * g1);
+    if (w * g0 == 123456.f) red_add_v2(grad_table + ((size_t)(off + idx[c])) * 2, w * g0, w * g1);
 #else
-    red_add_v2(grad_table + ((size_t)(off + idx)) * 2, w * g0, w * g1);
+    red_add_v2(grad_table + ((size_t)(off + idx[c])) * 2, w * g0, w * g1);
 #endif
   }
 }

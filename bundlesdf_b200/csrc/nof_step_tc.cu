@@ -155,6 +155,9 @@ __host__ __device__ inline Plan make_plan(int KE) {
 template <int NTU>
 __device__ __forceinline__ void wgrad_item(uint32_t dY, int Ky, uint32_t X, int Kx, int strip, int nt0, float (*acc)[4], float* bias2,
                                            bool do_bias, int lane) {
+#ifdef NOF_EXP_NO_WGRAD
+  return;
+#endif
   const uint32_t ones = 0x3C003C00u;
   const int pa = (lane & 7) + (lane >> 4) * 8, oa = strip * 16 + ((lane >> 3) & 1) * 8;       // A: rows p, cols o (dY^T)
   const int pb = (lane & 7) + ((lane >> 3) & 1) * 8, ib = (lane >> 4) * 8;                      // B: rows p, cols i
@@ -218,6 +221,9 @@ __device__ __forceinline__ void zero_acc(float (*acc)[4]) {
 template <int N, int K, int B_MN>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, int KA, uint32_t b_addr, int KB, uint64_t* bar) {
   constexpr uint32_t idesc = umma_idesc(128, N, 0, B_MN);
+#ifdef NOF_EXP_NO_TC
+  return;
+#endif
 #pragma unroll
   for (int ks = 0; ks < K / 16; ++ks) {
     const uint64_t ad = umma_desc(a_addr + ks * 256, 128, KA * 16);                      // two 16-byte k-chunks, 128 B apart
@@ -320,6 +326,9 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
 
   // wait for the MMA generation, make TMEM readable
   auto mma_wait = [&]() {
+#ifdef NOF_EXP_NO_TC
+    return;
+#endif
     tc_ok &= mbar_wait(bar_mma, phase);
     phase ^= 1u;
     tc_fence_after();
@@ -627,7 +636,8 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
       for (int j = 0; j < NH; j += 4) *reinterpret_cast<float4*>(dE + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
     tc_fence_before();
-    __syncthreads();                                        // dEnc rows visible to the two threads of each point
+    // With L = KE/2 levels split evenly, the columns this thread just pulled out of TMEM are exactly its own levels: no exchange.
+    if (!(2 * LH == KE / 2 && L == 2 * LH)) __syncthreads();   // dEnc rows visible to the two threads of each point
     // ============ 7. grid-gradient scatter + pose Jacobian for this thread's half of the levels
     {
       const float* dE = reinterpret_cast<const float*>(pX3) + (size_t)pt * 36;
@@ -647,20 +657,25 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
         }
       }
       if (a.p.need_pose_grad) {
-        float gtf[12];
+        // x = R (dir z) + t  =>  dL/dR[i][j] = dir[j] * sum_p gi z ,  dL/dt[i] = sum_p gi   (gi = 0.5 gx[i]: u = (x+1)/2):
+        // six warp sums instead of twelve (all lanes of a warp belong to one ray).
+        float st[6];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const float gi = 0.5f * gx[i];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) gtf[i * 4 + j] = gi * pc[j];
-          gtf[i * 4 + 3] = gi;
+          st[i] = warp_sum(gi);
+          st[3 + i] = warp_sum(gi * z);
         }
-#pragma unroll
-        for (int i = 0; i < 12; ++i) gtf[i] = warp_sum(gtf[i]);
         if (lane == 0 && rs.active && rs.frame != 0) {
 #pragma unroll
-          for (int i = 0; i < 12; ++i)
-            if (gtf[i] != 0.f) red_add(a.p.grad_tf + (size_t)rs.frame * 12 + i, gtf[i]);
+          for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float v = st[3 + i] * rs.dir[j];
+              if (v != 0.f) red_add(a.p.grad_tf + (size_t)rs.frame * 12 + i * 4 + j, v);
+            }
+            if (st[i] != 0.f) red_add(a.p.grad_tf + (size_t)rs.frame * 12 + i * 4 + 3, st[i]);
+          }
         }
       }
     }
