@@ -128,9 +128,9 @@ extern "C" size_t nof_step_workspace_bytes(const NofStep* p) {
   int sms = 148;
   nof_device_info(&sms, nullptr);
   Tiling t;
-  if (p->amp) { if (!amp_tiling(p, sms, &t)) return 0; return (size_t)t.blocks * MAX_L * 3 * (t.NW * 32) * 4 + 256; }
+  if (p->amp) { if (!amp_tiling(p, sms, &t)) return 0; return kWPackBytes + (size_t)t.blocks * MAX_L * 3 * (t.NW * 32) * 4 + 256; }
   if (!f32_tiling(p, sms, &t)) return 0;
-  return (size_t)t.blocks * MAX_L * 3 * 128 * 8 + 256;
+  return kWPackBytes + (size_t)t.blocks * MAX_L * 3 * 128 * 8 + 256;
 }
 
 extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
@@ -139,6 +139,7 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
   NOF_REQUIRE(p->N >= 0 && p->S >= 1, "nof_step_fused: bad sizes N=%d S=%d", p->N, p->S);
   NOF_REQUIRE(p->rays && p->tf && p->z_vals, "nof_step_fused: null batch pointer");
   NOF_REQUIRE(p->grad_table && p->grad_mlp && p->losses, "nof_step_fused: null output pointer");
+  NOF_REQUIRE((reinterpret_cast<uintptr_t>(p->grad_table) & 15u) == 0, "nof_step_fused: grad_table must be 16-byte aligned");
   NOF_REQUIRE(!p->need_pose_grad || p->grad_tf, "nof_step_fused: need_pose_grad without grad_tf");
   NOF_REQUIRE(p->workspace, "nof_step_fused: null workspace (see nof_step_workspace_bytes)");
   NOF_REQUIRE(p->ray_dim >= 10, "nof_step_fused: ray_dim=%d", p->ray_dim);
@@ -155,6 +156,8 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
   a.inv_N3 = 1.0f / (3.0f * (float)p->N);
   a.inv_NS = 1.0f / ((float)p->N * (float)p->S);
   a.inv_NS3 = a.inv_NS / 3.0f;
+  a.wpack = p->workspace;                                   // [0, kWPackBytes): packed fp16 MLP operands (tcgen05 path)
+  a.jws = static_cast<char*>(p->workspace) + kWPackBytes;   // then the per-CTA Jacobian scratch
   Tiling t;
   if (p->amp) {
     NOF_REQUIRE(amp_tiling(p, sms, &t), "nof_step_fused(amp): S=%d > 256 samples per ray not supported by the AMP tile (use amp: false)", p->S);

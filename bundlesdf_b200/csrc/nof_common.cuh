@@ -79,6 +79,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
+// 16-byte form: same L2 atomic-unit cost per lane as the 4- and 8-byte forms (profiles/red_bench.cu: ~180 G lane-ops/s for
+// random addresses whatever the width), so two adjacent table entries in one op halve the cost.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void red_add(float* addr, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }

@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
   const int LH = (L + 1) >> 1;
   const int l_beg = half ? LH : 0, l_end = half ? L : LH;
   const bool owner = half == 0;              // the thread that does the once-per-point work (compositing, seeds)
-  __half2* Jslot = reinterpret_cast<__half2*>(a.p.workspace) + (size_t)blockIdx.x * (MAX_L * 3) * PT;
+  __half2* Jslot = reinterpret_cast<__half2*>(a.jws) + (size_t)blockIdx.x * (MAX_L * 3) * PT;
   const int g8 = lane >> 2, t4 = lane & 3;
   const int row0 = warp * 16;                // MLP rows of this warp
 

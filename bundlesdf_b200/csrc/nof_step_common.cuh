@@ -22,7 +22,10 @@ struct StepArgs {
   int po[10];                   // element offsets of W1 b1 W2 b2 W3 b3 W4 b4 W5 b5 in the packed block
   int R, Sp, n_groups;          // rays per CTA, lanes per ray, number of ray groups
   float inv_N3, inv_NS, inv_NS3;
+  void* jws;                    // workspace: per-CTA Jacobian scratch
+  void* wpack;                  // workspace: fp16 MLP operands pre-packed for the tcgen05 kernel (kWPackBytes)
 };
+constexpr size_t kWPackBytes = 32 * 1024;
 
 struct RayS {                   // per-ray shared state
   float dir[3], u[3];           // camera-frame dir (non-unit) and its unit vector
@@ -252,14 +255,30 @@ __device__ __forceinline__ void scatter_level(float* grad_table, const LevelS& l
   }
   uint32_t idx[8];
   corner_indices(lv, l, pg, idx);
-  const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
+  const float wx0 = 1.f - fr[0], wx1 = fr[0];
+  const float wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
+  float* base = grad_table + (size_t)off * 2;
+  const bool pairable = (off & 1u) == 0u;                          // always true for grid.py's offsets (multiples of 8)
+  // The x / x+1 corners of a (y,z) pair are neighbours in memory whenever their entries differ only in bit 0 (dense levels:
+  // even entry; hashed levels: even x, because (x^A) and ((x|1)^A) differ in bit 0 only; level offsets are multiples of 8):
+  // then ONE 16-byte reduction carries both. The L2 atomic unit is the binding resource of the scatter and charges per lane
+  // operation, not per byte (profiles/red_bench.cu).
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float w = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t e0 = idx[2 * k], e1 = idx[2 * k + 1];
+    const float wyz = wy[k & 1] * wz[k >> 1];
+    const float w0 = wx0 * wyz, w1 = wx1 * wyz;
 #ifdef NOF_EXP_NO_RED     // profiling experiment only (profiles/README.md): what the kernel costs without the reductions
-    if (w * g0 == 123456.f) red_add_v2(grad_table + ((size_t)(off + idx[c])) * 2, w * g0, w * g1);
+    if (w0 * g0 == 123456.f) red_add_v2(base + (size_t)e0 * 2, w0 * g0, w1 * g1);
 #else
-    red_add_v2(grad_table + ((size_t)(off + idx[c])) * 2, w * g0, w * g1);
+    if ((e0 ^ e1) == 1u && pairable) {
+      const bool sw = (e0 & 1u) != 0u;                           // e0 is the odd entry: swap the halves
+      const float a0 = sw ? w1 : w0, a1 = sw ? w0 : w1;
+      red_add_v4(base + (size_t)(e0 & ~1u) * 2, a0 * g0, a0 * g1, a1 * g0, a1 * g1);
+    } else {
+      red_add_v2(base + (size_t)e0 * 2, w0 * g0, w0 * g1);
+      red_add_v2(base + (size_t)e1 * 2, w1 * g0, w1 * g1);
+    }
 #endif
   }
 }

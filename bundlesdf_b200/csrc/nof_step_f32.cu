@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(FT, 1) step_f32_kernel(const StepArgs a) {
 
   const int Sp = a.Sp, R = a.R, S = a.p.S;
   const int n_sub = grp_pts / FT;
-  float2* Jslot = reinterpret_cast<float2*>(a.p.workspace) + (size_t)blockIdx.x * (MAX_L * 3) * FT;
+  float2* Jslot = reinterpret_cast<float2*>(a.jws) + (size_t)blockIdx.x * (MAX_L * 3) * FT;
 
   for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
     if (tid < R) setup_ray(sRay[tid], a, grp * R + tid);

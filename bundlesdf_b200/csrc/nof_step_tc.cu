@@ -193,13 +193,18 @@ __device__ __forceinline__ void flush_item(float* G, int wofs, int bofs, int nco
 #pragma unroll
   for (int nt = 0; nt < CNT; ++nt)
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int o = strip * 16 + g8 + h * 8, i = (nt0 + nt) * 8 + 2 * t4 + c;
-        const float v = acc[nt][h * 2 + c];
-        if (o < nrows && i < ncols && v != 0.f) red_add(G + wofs + (size_t)o * ncols + i, v);
+    for (int h = 0; h < 2; ++h) {
+      const int o = strip * 16 + g8 + h * 8, i = (nt0 + nt) * 8 + 2 * t4;
+      const float v0 = acc[nt][h * 2], v1 = acc[nt][h * 2 + 1];
+      if (o >= nrows || i >= ncols) continue;
+      const size_t e = (size_t)wofs + (size_t)o * ncols + i;
+      if (i + 1 < ncols && (reinterpret_cast<uintptr_t>(G + e) & 7u) == 0u) {                       // the fragment's two columns in one 8-byte reduction
+        if (v0 != 0.f || v1 != 0.f) red_add_v2(G + e, v0, v1);
+      } else {
+        if (v0 != 0.f) red_add(G + e, v0);
+        if (i + 1 < ncols && v1 != 0.f) red_add(G + e + 1, v1);
       }
+    }
   if (has_bias && t4 == 0) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -234,6 +239,35 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, int
   umma_commit(bar);
 }
 
+// ------------------------------------------------------------------------------------------------ operand packing
+// fp32 packed parameters (nof_mlp_param_offsets order) -> the kernel's shared-memory image [W1 W2 W3 W4 W5 | biases]: fp16
+// weights in core-matrix order, zero padding, biases rounded through fp16 like torch autocast. One small CTA per step; the
+// 296 step CTAs then fetch the 21.5 KB image with one TMA bulk copy each instead of converting 9.6k weights each.
+template <int KE>
+__global__ void __launch_bounds__(1024) pack_mlp_kernel(const StepArgs a) {
+  const Plan sp = make_plan(KE);
+  unsigned char* out = static_cast<unsigned char*>(a.wpack);      // image offset 0 == plan offset sp.w1 (== 0)
+  const int tid = threadIdx.x, E = a.E, V = a.V;
+  for (int i = tid; i < (sp.x0 - sp.w1) / 4; i += 1024) reinterpret_cast<uint32_t*>(out)[i] = 0u;
+  if (tid == 0) *reinterpret_cast<int*>(out + kWPackBytes - 16) = 0;                 // tile ticket of the step kernel
+  __syncthreads();
+  const float* P = a.p.mlp;
+  auto put = [&](int base, int n, int k, int K, float v) { *reinterpret_cast<__half*>(out + base + cm_off(n, k, K)) = __float2half_rn(v); };
+  for (int i = tid; i < 64 * E; i += 1024) put(sp.w1, i / E, i % E, KE, P[a.po[0] + i]);
+  for (int i = tid; i < 16 * 64; i += 1024) put(sp.w2, i / 64, i % 64, 64, P[a.po[2] + i]);
+  const int K3 = V + 15;
+  for (int i = tid; i < 64 * K3; i += 1024) put(sp.w3, i / K3, i % K3, KC, P[a.po[4] + i]);
+  for (int i = tid; i < 64 * 64; i += 1024) put(sp.w4, i / 64, i % 64, 64, P[a.po[6] + i]);
+  for (int i = tid; i < 3 * 64; i += 1024) put(sp.w5, i / 64, i % 64, 64, P[a.po[8] + i]);
+  float* sB = reinterpret_cast<float*>(out + sp.bias);
+  auto rh = [](float v) { return __half2float(__float2half_rn(v)); };
+  for (int i = tid; i < 64; i += 1024) sB[i] = rh(P[a.po[1] + i]);
+  for (int i = tid; i < 16; i += 1024) sB[64 + i] = rh(P[a.po[3] + i]);
+  for (int i = tid; i < 64; i += 1024) sB[80 + i] = rh(P[a.po[5] + i]);
+  for (int i = tid; i < 64; i += 1024) sB[144 + i] = rh(P[a.po[7] + i]);
+  for (int i = tid; i < 3; i += 1024) sB[208 + i] = rh(P[a.po[9] + i]);
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int KE_>
 __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
@@ -247,7 +281,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem + sp.bar);
   uint64_t* bar_mma = bar_tma + 1;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + sp.tmem);
-  float* sStage = reinterpret_cast<float*>(smem + sp.x1);        // fp32 staging of the packed params (aliases X1, XC, X3..)
+  int* s_next = reinterpret_cast<int*>(s_tmem + 1);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t aW1 = sbase + sp.w1, aW2 = sbase + sp.w2, aW3 = sbase + sp.w3, aW4 = sbase + sp.w4, aW5 = sbase + sp.w5;
   const uint32_t aX0 = sbase + sp.x0, aX1 = sbase + sp.x1, aXC = sbase + sp.xc, aX3 = sbase + sp.x3, aX4 = sbase + sp.x4, aDO = sbase + sp.d_o;
@@ -272,31 +306,14 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
-  const int n_par = a.po[9] + 3;
-  const uint32_t par_bytes = (uint32_t)((n_par * 4 + 15) / 16 * 16);
+  // MLP operands: already fp16, core-matrix ordered and zero-padded (pack_mlp_kernel) — one bulk copy, no conversion
+  const uint32_t pack_bytes = (uint32_t)(sp.x0 - sp.w1);
   if (tid == 0) {
-    mbar_expect_tx(bar_tma, par_bytes);
-    tma_bulk_g2s(sStage, a.p.mlp, par_bytes, bar_tma);
+    mbar_expect_tx(bar_tma, pack_bytes);
+    tma_bulk_g2s(smem + sp.w1, a.wpack, pack_bytes, bar_tma);
   }
   init_levels(lv, a);
-  for (int i = tid; i < (sp.bias - sp.w1) / 4; i += NT) reinterpret_cast<uint32_t*>(smem + sp.w1)[i] = 0u;   // zero padding rows/cols
-  __syncthreads();
   bool tc_ok = mbar_wait(bar_tma, 0);
-  {
-    const float* P = sStage;
-    auto put = [&](int base, int n, int k, int K, float v) { *reinterpret_cast<__half*>(smem + base + cm_off(n, k, K)) = __float2half_rn(v); };
-    for (int i = tid; i < 64 * E; i += NT) put(sp.w1, i / E, i % E, KE, P[a.po[0] + i]);
-    for (int i = tid; i < 16 * 64; i += NT) put(sp.w2, i / 64, i % 64, 64, P[a.po[2] + i]);
-    const int K3 = V + 15;
-    for (int i = tid; i < 64 * K3; i += NT) put(sp.w3, i / K3, i % K3, KC, P[a.po[4] + i]);
-    for (int i = tid; i < 64 * 64; i += NT) put(sp.w4, i / 64, i % 64, 64, P[a.po[6] + i]);
-    for (int i = tid; i < 3 * 64; i += NT) put(sp.w5, i / 64, i % 64, 64, P[a.po[8] + i]);
-    for (int i = tid; i < 64; i += NT) sB[i] = __half2float(__float2half_rn(P[a.po[1] + i]));
-    for (int i = tid; i < 16; i += NT) sB[64 + i] = __half2float(__float2half_rn(P[a.po[3] + i]));
-    for (int i = tid; i < 64; i += NT) sB[80 + i] = __half2float(__float2half_rn(P[a.po[5] + i]));
-    for (int i = tid; i < 64; i += NT) sB[144 + i] = __half2float(__float2half_rn(P[a.po[7] + i]));
-    for (int i = tid; i < 8; i += NT) sB[208 + i] = (i < 3) ? __half2float(__float2half_rn(P[a.po[9] + i])) : 0.f;
-  }
   fence_async_smem();
   __syncthreads();
 
@@ -320,7 +337,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   const int LH = (L + 1) >> 1;
   const int l_beg = half ? LH : 0, l_end = half ? L : LH;
   const bool owner = half == 0;
-  __half2* Jslot = reinterpret_cast<__half2*>(a.p.workspace) + (size_t)blockIdx.x * (MAX_L * 3) * PT;
+  __half2* Jslot = reinterpret_cast<__half2*>(a.jws) + (size_t)blockIdx.x * (MAX_L * 3) * PT;
   const int g8 = lane >> 2, t4 = lane & 3;
   const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);     // TMEM address of this warp's lane quadrant
 
@@ -341,10 +358,16 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
     tc_fence_after();
   };
 
-  for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+  // Tiles (ray groups) are handed out dynamically: first one = blockIdx.x, then an atomic ticket (zeroed by pack_mlp_kernel).
+  // 2048 tiles over 296 CTAs of uneven cost (invalid samples skip gather and scatter): -8.5 % vs the static round-robin. Starting
+  // the second CTA of each SM half a tile late was tried and does not help.
+  int* tile_ticket = reinterpret_cast<int*>(static_cast<char*>(a.wpack) + kWPackBytes - 16);
+  for (int grp = blockIdx.x; grp < a.n_groups;) {
     // ============ 1. ray setup
     if (tid < R) setup_ray(sRay[tid], a, grp * R + tid);
+    if (tid == NT - 1) *s_next = (int)gridDim.x + atomicAdd(tile_ticket, 1);
     __syncthreads();
+    grp = *s_next;                                          // the NEXT tile (this one's rays are already staged)
     const RayS& rs = sRay[rl];
     const bool active = rs.active && sidx < S;
     const float z = active ? a.p.z_vals[(size_t)rs.ray * S + sidx] : 0.f;
@@ -747,6 +770,8 @@ static int launch_tc(const StepArgs& a, int blocks, cudaStream_t st) {
     cudaFuncSetAttribute(tc::step_tc_kernel<KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     once = true;
   }
+  static_assert((size_t)(64 * KE * 2 + 16 * 64 * 2 + 64 * KC * 2 + 64 * 64 * 2 + 16 * 64 * 2 + 216 * 4 + 6 * 128 + 16) <= kWPackBytes, "wpack too small");
+  tc::pack_mlp_kernel<KE><<<1, 1024, 0, st>>>(a);
   tc::step_tc_kernel<KE><<<blocks, tc::NT, smem, st>>>(a);
   return check_launch("step_tc_kernel");
 }
