@@ -122,9 +122,11 @@ template <> struct TmemLd<32> {
 __device__ __forceinline__ uint32_t cm_off(int r, int k, int K) { return (uint32_t)((r >> 3) * (K * 16) + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2); }
 
 constexpr int PT = 128, NT = 256, NWARP = 8;
+constexpr int DES = PT + PT / 8;                 // padded point stride of the transposed dEnc / z arrays: index pt + pt/8
+__device__ __forceinline__ int des_idx(int pt) { return pt + (pt >> 3); }
 
 struct Plan {
-  int w1, w2, w3, w4, w5, bias, x0, x1, xc, x3, x4, d_o, out, rays, lv, bar, tmem, total;
+  int w1, w2, w3, w4, w5, bias, x0, x1, xc, x3, x4, d_o, out, zs, rays, lv, bar, tmem, total;
 };
 __host__ __device__ inline Plan make_plan(int KE) {
   Plan s;
@@ -139,10 +141,11 @@ __host__ __device__ inline Plan make_plan(int KE) {
   s.x0 = take(PT * KE * 2);
   s.x1 = take(PT * 64 * 2);
   s.xc = take(PT * KC * 2);
-  s.x3 = take(PT * 64 * 2);                 // x3|x4 also hold dEnc fp32 [PT][36] at the end of the backward
+  s.x3 = take(PT * 64 * 2);                 // x3|x4 also hold dEnc fp32 [KE][DES] (transposed) at the end of the backward
   s.x4 = take(PT * 64 * 2);
   s.d_o = take(PT * 16 * 2);
   s.out = take(PT * 4 * 4);
+  s.zs = take(2 * DES * 4);                  // z and the valid flag of every point, in the scatter's padded order
   s.rays = take(MAX_R * (int)sizeof(RayS));
   s.lv = take((int)sizeof(LevelS));
   s.bar = take(64);                          // [0] TMA staging barrier, [1] MMA completion barrier
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   const Plan sp = make_plan(KE);
   float* sB = reinterpret_cast<float*>(smem + sp.bias);
   float* sOut = reinterpret_cast<float*>(smem + sp.out);
+  float* sZ = reinterpret_cast<float*>(smem + sp.zs);
   RayS* sRay = reinterpret_cast<RayS*>(smem + sp.rays);
   LevelS& lv = *reinterpret_cast<LevelS*>(smem + sp.lv);
   uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem + sp.bar);
@@ -543,6 +547,8 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
       overflow |= !(fabsf(s0) <= 65504.f) || !(fabsf(s1) <= 65504.f) || !(fabsf(s2) <= 65504.f) || !(fabsf(dsdf_s) <= 65504.f);
       *reinterpret_cast<uint4*>(pDO + cm_off(pt, 0, 16)) = make_uint4(pack_h2(s0, s1), pack_h2(s2, 0.f), 0u, 0u);
       *reinterpret_cast<uint4*>(pDO + cm_off(pt, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
+      sZ[des_idx(pt)] = z;
+      sZ[DES + des_idx(pt)] = valid ? 1.f : 0.f;
     }
     sync_for_mma();                                         // (S0) dOut visible to the warps and to the tensor core
 
@@ -654,50 +660,122 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
       constexpr int NH = KE / 2;                            // columns per thread
       float v[NH];
       TmemLd<NH>::ld(trow + half * NH, v);
-      float* dE = reinterpret_cast<float*>(pX3) + (size_t)pt * 36 + half * NH;   // [PT][36] fp32: spills into X4 (dead)
+      float* dE = reinterpret_cast<float*>(pX3) + des_idx(pt);                 // transposed: [column][DES], spills into X4 (dead)
 #pragma unroll
-      for (int j = 0; j < NH; j += 4) *reinterpret_cast<float4*>(dE + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int j = 0; j < NH; ++j) dE[(half * NH + j) * DES] = v[j];
     }
     tc_fence_before();
-    // With L = KE/2 levels split evenly, the columns this thread just pulled out of TMEM are exactly its own levels: no exchange.
-    if (!(2 * LH == KE / 2 && L == 2 * LH)) __syncthreads();   // dEnc rows visible to the two threads of each point
-    // ============ 7. grid-gradient scatter + pose Jacobian for this thread's half of the levels
+    __syncthreads();                                        // dEnc visible to the scatter's (8 samples x 1 level) threads
+    // ============ 7. grid-gradient scatter + pose Jacobian. Thread = 8 CONSECUTIVE samples of one ray x ONE level (warp w: levels
+    // 2w, 2w+1; lane & 15: sample group). Consecutive samples mostly fall into the same grid cell (C2: one new cell every 17 samples
+    // at the coarsest level, every 2.4 at the finest), so the 8 corner contributions are summed in registers over the run and go out
+    // as ONE set of reductions per run: ~3.5x fewer operations on the L2 atomic unit, which is what bounds the scatter
+    // (profiles/red_bench.cu: ~180 G lane-ops/s whatever the operand width).
     {
-      const float* dE = reinterpret_cast<const float*>(pX3) + (size_t)pt * 36;
-      float gx[3] = {0.f, 0.f, 0.f};
-      if (valid) {
-#pragma unroll 2
-        for (int l = l_beg; l < l_end; ++l) {
-          const float2 g = *reinterpret_cast<const float2*>(dE + 2 * l);
-          if (g.x != 0.f || g.y != 0.f) scatter_level(a.p.grad_table, lv, l, u, g.x, g.y);
-          if (a.p.need_pose_grad) {
+      const int sg = lane & 15, l = 2 * warp + (lane >> 4);
+      const int p0 = 8 * sg;
+      const RayS& r8 = sRay[p0 / Sp];
+      float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (l < L) {
+        const float scale = lv.scale[l];
+        const uint32_t off = lv.off[l];
+        const float* dE0 = reinterpret_cast<const float*>(pX3) + (size_t)(2 * l) * DES;
+        float acc[8][2];
+        uint32_t cpg[3] = {0u, 0u, 0u};
+        bool have = false;
+#pragma unroll 1
+        for (int j = 0; j <= 8; ++j) {
+          bool live = false;
+          uint32_t pg[3] = {0u, 0u, 0u};
+          float fr[3] = {0.f, 0.f, 0.f}, g0 = 0.f, g1 = 0.f;
+          if (j < 8) {
+            const int q = p0 + j, qi = des_idx(q);
+            if (sZ[DES + qi] != 0.f) {
+              g0 = dE0[qi];
+              g1 = dE0[DES + qi];
+              const float zq = sZ[qi];
+              float pcq[3], xq[3];
+              world_point(r8, zq, pcq, xq);                 // identical arithmetic to the gather: same cell, same weights
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const float2 j = __half22float2(Jslot[(size_t)(l * 3 + d) * PT + pt]);
-              gx[d] = fmaf(g.x, j.x, fmaf(g.y, j.y, gx[d]));
+              for (int d = 0; d < 3; ++d) {
+                const float pp = fmaf((xq[d] + 1.0f) * 0.5f, scale, 0.5f);
+                const float fl = floorf(pp);
+                pg[d] = (uint32_t)fl;
+                fr[d] = pp - fl;
+              }
+              live = (g0 != 0.f || g1 != 0.f);
+              if (a.p.need_pose_grad && live) {
+                float gx[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                  const float2 jj = __half22float2(Jslot[(size_t)(l * 3 + d) * PT + q]);
+                  gx[d] = 0.5f * fmaf(g0, jj.x, g1 * jj.y);
+                  st[d] += gx[d];
+                  st[3 + d] = fmaf(gx[d], zq, st[3 + d]);
+                }
+              }
+            }
+          }
+          const bool newcell = live && (!have || pg[0] != cpg[0] || pg[1] != cpg[1] || pg[2] != cpg[2]);
+          if (have && (newcell || j == 8)) {                // the run ended: one set of reductions for all its samples
+            uint32_t idx[8];
+            corner_indices(lv, l, cpg, idx);
+            float* base = a.p.grad_table + (size_t)off * 2;
+            const bool pairable = (off & 1u) == 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t e0 = idx[2 * k], e1 = idx[2 * k + 1];
+#ifdef NOF_EXP_NO_RED
+              if (acc[2 * k][0] == 123456.f) red_add_v2(base + (size_t)e0 * 2, acc[2 * k][0], acc[2 * k][1]);
+#else
+              if ((e0 ^ e1) == 1u && pairable) {
+                const bool sw = (e0 & 1u) != 0u;             // e0 is the odd entry: its values go to the upper half
+                red_add_v4(base + (size_t)(e0 & ~1u) * 2, sw ? acc[2 * k + 1][0] : acc[2 * k][0], sw ? acc[2 * k + 1][1] : acc[2 * k][1],
+                           sw ? acc[2 * k][0] : acc[2 * k + 1][0], sw ? acc[2 * k][1] : acc[2 * k + 1][1]);
+              } else {
+                red_add_v2(base + (size_t)e0 * 2, acc[2 * k][0], acc[2 * k][1]);
+                red_add_v2(base + (size_t)e1 * 2, acc[2 * k + 1][0], acc[2 * k + 1][1]);
+              }
+#endif
+            }
+            have = false;
+          }
+          if (newcell) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c][0] = acc[c][1] = 0.f;
+            cpg[0] = pg[0]; cpg[1] = pg[1]; cpg[2] = pg[2];
+            have = true;
+          }
+          if (live) {
+            const float wx[2] = {1.f - fr[0], fr[0]}, wy[2] = {1.f - fr[1], fr[1]}, wz[2] = {1.f - fr[2], fr[2]};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float w = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
+              acc[c][0] = fmaf(w, g0, acc[c][0]);
+              acc[c][1] = fmaf(w, g1, acc[c][1]);
             }
           }
         }
       }
       if (a.p.need_pose_grad) {
-        // x = R (dir z) + t  =>  dL/dR[i][j] = dir[j] * sum_p gi z ,  dL/dt[i] = sum_p gi   (gi = 0.5 gx[i]: u = (x+1)/2):
-        // six warp sums instead of twelve (all lanes of a warp belong to one ray).
-        float st[6];
+        // x = R (dir z) + t  =>  dL/dR[i][j] = dir[j] * sum gi z ,  dL/dt[i] = sum gi  (gi = 0.5 gx[i]: u = (x+1)/2). Sum over the lanes
+        // of the same ray: Sp/8 sample groups (16, 8 or 4 lanes) in each half-warp, then across the two level halves.
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const float gi = 0.5f * gx[i];
-          st[i] = warp_sum(gi);
-          st[3 + i] = warp_sum(gi * z);
+        for (int i = 0; i < 6; ++i) {
+          float v = st[i];
+          for (int o = 1; o < Sp / 8; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          st[i] = v;
         }
-        if (lane == 0 && rs.active && rs.frame != 0) {
+        if ((lane & (Sp / 8 - 1)) == 0 && lane < 16 && r8.active && r8.frame != 0) {
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-              const float v = st[3 + i] * rs.dir[j];
-              if (v != 0.f) red_add(a.p.grad_tf + (size_t)rs.frame * 12 + i * 4 + j, v);
+              const float v = st[3 + i] * r8.dir[j];
+              if (v != 0.f) red_add(a.p.grad_tf + (size_t)r8.frame * 12 + i * 4 + j, v);
             }
-            if (st[i] != 0.f) red_add(a.p.grad_tf + (size_t)rs.frame * 12 + i * 4 + 3, st[i]);
+            if (st[i] != 0.f) red_add(a.p.grad_tf + (size_t)r8.frame * 12 + i * 4 + 3, st[i]);
           }
         }
       }
