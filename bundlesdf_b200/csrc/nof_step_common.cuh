@@ -86,6 +86,9 @@ __device__ __forceinline__ void init_levels(LevelS& lv, const StepArgs& a) {
   }
 }
 
+// `%` for table sizes that are not powers of two: never the case for grid.py tables, so keep the division sequence out of line.
+static __device__ __noinline__ uint32_t umod_cold(uint32_t a, uint32_t b) { return a % b; }
+
 // Table entries of the 8 corners of one cell (gridencoder.cu:62-84): corner c = (c&1, (c>>1)&1, (c>>2)&1). The level is
 // warp-uniform, so the dense / hashed split is a real branch; both forms are incremental (uint32 wrap-around arithmetic is
 // exact: (y+1)*p == y*p + p mod 2^32), ~20 integer instructions per cell instead of ~45.
@@ -110,7 +113,7 @@ __device__ __forceinline__ void corner_indices(const LevelS& lv, int l, const ui
     } else {
       const uint32_t hs = lv.hsize[l];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) idx[c] %= hs;
+      for (int c = 0; c < 8; ++c) idx[c] = umod_cold(idx[c], hs);
     }
   }
 }

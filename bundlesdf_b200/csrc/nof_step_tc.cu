@@ -41,6 +41,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // Bounded wait: never hangs the GPU. Returns false on timeout (the caller raises the device error flag).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t phase) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
   for (int it = 0; it < (1 << 22); ++it) {
     uint32_t ok;
     asm volatile(
@@ -145,7 +146,7 @@ __host__ __device__ inline Plan make_plan(int KE) {
   s.x4 = take(PT * 64 * 2);
   s.d_o = take(PT * 16 * 2);
   s.out = take(PT * 4 * 4);
-  s.zs = take(2 * DES * 4);                  // z and the valid flag of every point, in the scatter's padded order
+  s.zs = take(5 * DES * 4);                  // z, valid flag and u[3] of every point, in the scatter's padded order
   s.rays = take(MAX_R * (int)sizeof(RayS));
   s.lv = take((int)sizeof(LevelS));
   s.bar = take(64);                          // [0] TMA staging barrier, [1] MMA completion barrier
@@ -382,6 +383,11 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
     for (int d = 0; d < 3; ++d) u[d] = (x[d] + 1.0f) * 0.5f;
     const float w_raw = active ? raw_weight(a, z, rs.depth) : 0.f;
     if (owner) {
+      const int qi = des_idx(pt);                           // for the scatter, whose threads own other points
+      sZ[qi] = z;
+      sZ[DES + qi] = valid ? 1.f : 0.f;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) sZ[(2 + d) * DES + qi] = u[d];
       const float ws = warp_sum(w_raw);
       const unsigned anyv = __ballot_sync(0xffffffffu, valid);
       if (lane == 0) {
@@ -547,8 +553,6 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
       overflow |= !(fabsf(s0) <= 65504.f) || !(fabsf(s1) <= 65504.f) || !(fabsf(s2) <= 65504.f) || !(fabsf(dsdf_s) <= 65504.f);
       *reinterpret_cast<uint4*>(pDO + cm_off(pt, 0, 16)) = make_uint4(pack_h2(s0, s1), pack_h2(s2, 0.f), 0u, 0u);
       *reinterpret_cast<uint4*>(pDO + cm_off(pt, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
-      sZ[des_idx(pt)] = z;
-      sZ[DES + des_idx(pt)] = valid ? 1.f : 0.f;
     }
     sync_for_mma();                                         // (S0) dOut visible to the warps and to the tensor core
 
@@ -694,11 +698,9 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
               g0 = dE0[qi];
               g1 = dE0[DES + qi];
               const float zq = sZ[qi];
-              float pcq[3], xq[3];
-              world_point(r8, zq, pcq, xq);                 // identical arithmetic to the gather: same cell, same weights
 #pragma unroll
-              for (int d = 0; d < 3; ++d) {
-                const float pp = fmaf((xq[d] + 1.0f) * 0.5f, scale, 0.5f);
+              for (int d = 0; d < 3; ++d) {                 // same u as the gather used: same cell, same weights
+                const float pp = fmaf(sZ[(2 + d) * DES + qi], scale, 0.5f);
                 const float fl = floorf(pp);
                 pg[d] = (uint32_t)fl;
                 fr[d] = pp - fl;
@@ -721,21 +723,14 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
             uint32_t idx[8];
             corner_indices(lv, l, cpg, idx);
             float* base = a.p.grad_table + (size_t)off * 2;
-            const bool pairable = (off & 1u) == 0u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t e0 = idx[2 * k], e1 = idx[2 * k + 1];
 #ifdef NOF_EXP_NO_RED
               if (acc[2 * k][0] == 123456.f) red_add_v2(base + (size_t)e0 * 2, acc[2 * k][0], acc[2 * k][1]);
-#else
-              if ((e0 ^ e1) == 1u && pairable) {
-                const bool sw = (e0 & 1u) != 0u;             // e0 is the odd entry: its values go to the upper half
-                red_add_v4(base + (size_t)(e0 & ~1u) * 2, sw ? acc[2 * k + 1][0] : acc[2 * k][0], sw ? acc[2 * k + 1][1] : acc[2 * k][1],
-                           sw ? acc[2 * k][0] : acc[2 * k + 1][0], sw ? acc[2 * k][1] : acc[2 * k + 1][1]);
-              } else {
-                red_add_v2(base + (size_t)e0 * 2, acc[2 * k][0], acc[2 * k][1]);
-                red_add_v2(base + (size_t)e1 * 2, acc[2 * k + 1][0], acc[2 * k + 1][1]);
-              }
+#else   // one 8-byte reduction per corner: pairing x/x+1 into 16-byte ones (scatter_level) costs more issue slots than it saves here
+              red_add_v2(base + (size_t)e0 * 2, acc[2 * k][0], acc[2 * k][1]);
+              red_add_v2(base + (size_t)e1 * 2, acc[2 * k + 1][0], acc[2 * k + 1][1]);
 #endif
             }
             have = false;
