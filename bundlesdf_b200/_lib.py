@@ -54,6 +54,7 @@ _SIGS = {
     'nof_mlp_param_offsets': (C.c_int, [C.c_int, C.c_int, C.POINTER(_i32)]),
     'nof_step_workspace_bytes': (_sz, [C.POINTER(NofStep)]),
     'nof_step_fused': (C.c_int, [C.POINTER(NofStep), _vp]),
+    'nof_set_amp_impl': (C.c_int, [C.c_int]),
     'nof_adam_step': (C.c_int, [C.POINTER(NofAdamSeg), C.c_int, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     'nof_query_sdf': (C.c_int, [C.POINTER(NofStep), _vp, _vp, _i64, _vp]),
 }

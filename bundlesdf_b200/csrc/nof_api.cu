@@ -35,13 +35,13 @@ int step_tc_dispatch(const StepArgs& a, int blocks, cudaStream_t st);
 
 // The 128-point AMP tile has two implementations of the MLP GEMMs: tcgen05/TMEM (default) and mma.sync (NOF_AMP_IMPL=mma,
 // kept as the cross-check; larger tiles always use it).
+static int g_amp_impl = -1;
 static bool amp_use_tcgen05() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_amp_impl < 0) {
     const char* e = getenv("NOF_AMP_IMPL");
-    v = (e && strcmp(e, "mma") == 0) ? 0 : 1;
+    g_amp_impl = (e && strcmp(e, "mma") == 0) ? 0 : 1;
   }
-  return v == 1;
+  return g_amp_impl == 1;
 }
 
 static void mlp_offsets(int E, int V, int32_t o[10], size_t* total) {
@@ -84,6 +84,11 @@ static bool f32_tiling(const NofStep* p, int sms, Tiling* t) {
 using namespace nof;
 
 extern "C" int nof_version(void) { return NOF_VERSION; }
+extern "C" int nof_set_amp_impl(int impl) {
+  const int old = nof::amp_use_tcgen05() ? 1 : 0;
+  nof::g_amp_impl = impl ? 1 : 0;
+  return old;
+}
 extern "C" const char* nof_last_error(void) { return g_err; }
 
 extern "C" int nof_device_info(int* sm_count, int* max_smem_optin) {

@@ -60,12 +60,26 @@ CASES = [
     (4, 128, 14, 32, 32, 64, 0, {}),                                   # C1-shaped (S=64, L=4)
     (16, 256, 12, 64, 64, 48, 0, dict(invalid_frac=0.1, type1_frac=0.1)),   # C2/C3-shaped (S=128, L=16), invalid-depth + uncertain rays
     (16, 256, 12, 128, 64, 18, 2, {}),                                 # reference default split 128+64, frame features on
+    (4, 128, 14, 16, 16, 30, 0, {}),                                   # S=32: four rays per tile, ragged last tile
+    (4, 128, 14, 24, 20, 33, 1, dict(invalid_frac=0.2)),               # S=44: padded lanes inside the tile, odd ray count, ff=1
 ]
 
 
+@pytest.fixture
+def amp_impl(request):
+    """Select the AMP tile implementation through the C ABI (include/nof.h nof_set_amp_impl) and restore it afterwards."""
+    from bundlesdf_b200 import _lib
+    lib = _lib.load()
+    old = lib.nof_set_amp_impl(1 if request.param == 'tcgen05' else 0)
+    yield request.param
+    lib.nof_set_amp_impl(old)
+
+
 @pytest.mark.parametrize('L,finest,log2T,S_occ,S_d,N,ff,kw', CASES)
-@pytest.mark.parametrize('amp', [False, True])
-def test_fused_step_matches_oracle(L, finest, log2T, S_occ, S_d, N, ff, kw, amp):
+@pytest.mark.parametrize('amp,amp_impl', [(False, 'tcgen05'), (True, 'tcgen05'), (True, 'mma')], indirect=['amp_impl'])
+def test_fused_step_matches_oracle(L, finest, log2T, S_occ, S_d, N, ff, kw, amp, amp_impl):
+    if amp and amp_impl == 'mma' and S_occ + S_d > 128:
+        pytest.skip('S > 128 always runs the mma.sync tile: covered by the tcgen05-default case')
     cfg = helpers.make_cfg(L, finest, log2T, S_occ, S_d, ff=ff)
     if ff:
         cfg['fs_rgb_weight'] = 0.5
