@@ -382,17 +382,17 @@ def main():
         traffic = json.load(open(os.path.join(REPO, 'profiles', 'step_kernel_traffic.json'))).get(args.config)
     except Exception:
         pass
-    roofline = {'bound': 'hbm', 'kernel': 'step_amp_kernel (fused forward+loss+backward)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+    roofline = {'bound': 'hbm', 'kernel': 'step_tc_kernel (fused forward+loss+backward; tcgen05 MLP chain) incl. its 1-CTA pack_mlp_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'algorithmic_bytes_per_launch': abytes, 'kernel_ms': t_k * 1e3,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s (of fallback)',
-                'note': 'algorithmic bytes assume no cache credit; the 17.4 MB fp16 table is L2-resident, so DRAM traffic is far below this'}
+                'note': 'algorithmic bytes assume no cache credit; the fp16 table is L2-resident, so DRAM traffic is far below this; the kernel is bound by instruction issue and the L2 atomic unit (DESIGN.md), not by HBM'}
 
     line = {'metric': 'nerf_train_rays_per_s', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': 1e3 * t / args.steps, 'steps_per_s': args.steps / t, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f16 (fp32 accumulate, fp32 master weights)', 'data': 'synthetic', 'config': config, 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': N * 12 * 4, 'd2h_bytes_per_step': 32, 'steps': e2e_steps,
                     'ms_per_step': 1e3 * t_e2e / e2e_steps},
-            'gpu_launches': 7 * args.steps, 'roofline': roofline, 'ray_pool': int(runner.rays.shape[0]),
+            'gpu_launches': 8 * args.steps, 'roofline': roofline, 'ray_pool': int(runner.rays.shape[0]),
             'setup_s': round(t_setup, 1)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         tc, nr = cpu_baseline_run(c, 3, 1, args.cpu_rays)

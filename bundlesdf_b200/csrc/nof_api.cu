@@ -138,6 +138,12 @@ extern "C" size_t nof_step_workspace_bytes(const NofStep* p) {
   return kWPackBytes + (size_t)t.blocks * MAX_L * 3 * 128 * 8 + 256;
 }
 
+// Per-step results start from zero (the tcgen05 path does this inside its operand-packing kernel instead).
+static void zero_step_outputs(const NofStep* p, cudaStream_t st) {
+  cudaMemsetAsync(p->losses, 0, 8 * sizeof(float), st);
+  if (p->grad_tf) cudaMemsetAsync(p->grad_tf, 0, (size_t)p->F * 12 * sizeof(float), st);
+}
+
 extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
   int rc = validate_step(p, "nof_step_fused");
   if (rc) return rc;
@@ -174,12 +180,14 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
     }
     NOF_REQUIRE(step_amp_smem(t.NW * 32, a.KE) <= (size_t)smem_max, "nof_step_fused(amp): needs %zu B shared memory, device allows %d",
                 step_amp_smem(t.NW * 32, a.KE), smem_max);
+    zero_step_outputs(p, as_stream(stream));
     return step_amp_dispatch(a, t.NW, t.blocks, as_stream(stream));
   }
   NOF_REQUIRE(f32_tiling(p, sms, &t), "nof_step_fused(fp32): S=%d not supported (R*ceil32(S) must be <= 1024 with R<=4)", p->S);
   a.R = t.R; a.Sp = t.Sp; a.n_groups = t.n_groups;
   NOF_REQUIRE(step_f32_smem(a.E, a.V, a.R * a.Sp) <= (size_t)smem_max, "nof_step_fused(fp32): shared memory %zu > %d",
               step_f32_smem(a.E, a.V, a.R * a.Sp), smem_max);
+  zero_step_outputs(p, as_stream(stream));
   return step_f32_dispatch(a, t.blocks, as_stream(stream));
 }
 

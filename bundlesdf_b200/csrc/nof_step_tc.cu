@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(1024) pack_mlp_kernel(const StepArgs a) {
   const int tid = threadIdx.x, E = a.E, V = a.V;
   for (int i = tid; i < (sp.x0 - sp.w1) / 4; i += 1024) reinterpret_cast<uint32_t*>(out)[i] = 0u;
   if (tid == 0) *reinterpret_cast<int*>(out + kWPackBytes - 16) = 0;                 // tile ticket of the step kernel
+  if (tid < 8) a.p.losses[tid] = 0.f;                                                // per-step results start from zero
+  if (a.p.grad_tf) for (int i = tid; i < a.p.F * 12; i += 1024) a.p.grad_tf[i] = 0.f;
   __syncthreads();
   const float* P = a.p.mlp;
   auto put = [&](int base, int n, int k, int K, float v) { *reinterpret_cast<__half*>(out + base + cm_off(n, k, K)) = __float2half_rn(v); };

@@ -436,10 +436,7 @@ class NerfRunner:
         sb.set(rays=batch)
         for k in ('rgb_map', 'raw', 'valid_samples', 'weights'):
             sb.set(**{k: (taps.get(k) if taps else None)})
-        b['losses'].zero_()
-        if pa is not None:
-            b['grad_tf'].zero_()
-        sb.launch()
+        sb.launch()                                         # zeroes b['losses'] and b['grad_tf'] itself
         if pa is not None:
             ops.pose_backward(pa.data.data, self.c2w_array, b['grad_tf'], self.adam_segs['pose']['grad'].view(-1, 6), cfg['max_trans'] * sc,
                               cfg['max_rot'], self.amp_scaler.state if self.amp_scaler.enabled else None)

@@ -167,7 +167,8 @@ typedef struct {
   float rgb_weight, fs_weight, empty_weight, trunc_weight, fs_sdf, fs_rgb_weight, first_frame_weight;
   const float* loss_scale;      /* device scalar (GradScaler, nerf_runner.py:159) or NULL = 1 */
   int need_pose_grad;           /* cfg optimize_poses */
-  /* outputs — all ACCUMULATED into with atomics, caller zero-fills (nof_adam_step re-zeros grads) */
+  /* outputs. The parameter gradients (grad_table, grad_mlp, grad_feat) are ACCUMULATED into with atomics: the caller zero-fills
+   * them once and nof_adam_step re-zeros them. grad_tf and losses are per-step results: the call zeroes them itself. */
   float* grad_table;            /* [sO,C] fp32, scaled by loss_scale */
   float* grad_mlp;              /* packed like `mlp`, scaled by loss_scale */
   float* grad_tf;               /* [F,12], scaled */
