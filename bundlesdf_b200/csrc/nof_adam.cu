@@ -23,9 +23,40 @@ struct AdamArgs {
   float beta1, beta2, eps;
 };
 
-__global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a, const int32_t* __restrict__ step_ptr,
-                                                            const float* __restrict__ scale_state,
-                                                            const int32_t* __restrict__ found_inf) {
+// GradScaler.update() (growth_factor 2, backoff 0.5, growth_interval 2000) + step counter + RNG tick + flag reset.
+__device__ __forceinline__ void adam_finish(int32_t* step_ptr, float* scale_state, int32_t* found_inf, unsigned long long* tick, float beta1,
+                                            float beta2) {
+  if (tick) *tick += 1ull;
+  const bool inf = found_inf && (*found_inf != 0);
+  if (!inf && step_ptr) *step_ptr += 1;
+  if (step_ptr) {                                           // cache the NEXT update's bias corrections (torch computes them in fp64)
+    const int next = *step_ptr + 1;
+    step_ptr[1] = __float_as_int((float)(1.0 / (1.0 - pow((double)beta1, (double)next))));
+    step_ptr[2] = __float_as_int((float)sqrt(1.0 - pow((double)beta2, (double)next)));
+    step_ptr[3] = next;
+  }
+  if (scale_state) {
+    if (inf) {
+      scale_state[0] *= 0.5f;
+      scale_state[1] = 0.f;
+    } else {
+      scale_state[1] += 1.f;
+      if (scale_state[1] >= 2000.f) {
+        scale_state[0] *= 2.0f;
+        scale_state[1] = 0.f;
+      }
+    }
+  }
+  if (found_inf) *found_inf = 0;
+}
+// only when the caller passes no step buffer (no place for the completion counter) or there is nothing to update
+__global__ void adam_finish_kernel(int32_t* step_ptr, float* scale_state, int32_t* found_inf, unsigned long long* tick, float beta1,
+                                   float beta2) {
+  adam_finish(step_ptr, scale_state, found_inf, tick, beta1, beta2);
+}
+
+__global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a, int32_t* step_ptr, float* scale_state, int32_t* found_inf,
+                                                            unsigned long long* tick) {
   const uint32_t tile = blockIdx.x;
   int si = 0;
 #pragma unroll
@@ -53,23 +84,25 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a, co
       v[j] = __ldcs(reinterpret_cast<const float4*>(V + idx[j]));
     }
   }
-  // ---- per-launch scalars: one thread does the FP64 bias corrections while the loads above are in flight
-  __shared__ float s_bc[3];
-  if (threadIdx.x == 0) {
-    const int step = (step_ptr ? __ldg(step_ptr) : 0) + 1;  // this update's 1-based step
-    if (step_ptr && __ldg(step_ptr + 3) == step) {          // bias corrections cached by the previous adam_finish_kernel
-      s_bc[0] = __int_as_float(__ldg(step_ptr + 1));
-      s_bc[1] = __int_as_float(__ldg(step_ptr + 2));
-    } else {                                                // first step / externally modified counter: FP64 pow here
+  // ---- per-launch scalars: every thread reads them itself (independent loads, L1 hits after the first CTA of the SM) while its
+  // data loads are in flight; only a cache miss of the bias corrections (first update, restored counter) takes the FP64 path
+  const int step = (step_ptr ? step_ptr[0] : 0) + 1;        // this update's 1-based step
+  const bool cached = step_ptr && step_ptr[3] == step;      // bias corrections left by the previous call's adam_finish
+  float inv_bc1 = cached ? __int_as_float(step_ptr[1]) : 0.f, sqrt_bc2 = cached ? __int_as_float(step_ptr[2]) : 0.f;
+  const float inv_scale = scale_state ? 1.0f / scale_state[0] : 1.0f;
+  const bool skip = found_inf && (*found_inf != 0);
+  const float lr = sg.lr_ptr ? *sg.lr_ptr : sg.lr;
+  if (!cached) {                                            // CTA-uniform
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {
       s_bc[0] = (float)(1.0 / (1.0 - pow((double)a.beta1, (double)step)));
       s_bc[1] = (float)sqrt(1.0 - pow((double)a.beta2, (double)step));
     }
-    s_bc[2] = scale_state ? 1.0f / __ldg(scale_state) : 1.0f;
+    __syncthreads();
+    inv_bc1 = s_bc[0];
+    sqrt_bc2 = s_bc[1];
   }
-  __syncthreads();
-  const float inv_bc1 = s_bc[0], sqrt_bc2 = s_bc[1], inv_scale = s_bc[2];
-  const bool skip = found_inf && (__ldg(found_inf) != 0);
-  const float step_size = (sg.lr_ptr ? __ldg(sg.lr_ptr) : sg.lr) * inv_bc1;
+  const float step_size = lr * inv_bc1;
   const float b1 = a.beta1, b2 = a.beta2, eps = a.eps;
 
 #pragma unroll
@@ -110,33 +143,16 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a, co
       }
     }
   }
-}
-
-// GradScaler.update() (growth_factor 2, backoff 0.5, growth_interval 2000) + step counter + RNG tick + flag reset.
-__global__ void adam_finish_kernel(int32_t* step_ptr, float* scale_state, int32_t* found_inf, unsigned long long* tick, float beta1,
-                                   float beta2) {
-  if (tick) *tick += 1ull;
-  const bool inf = found_inf && (*found_inf != 0);
-  if (!inf && step_ptr) *step_ptr += 1;
-  if (step_ptr) {                                           // cache the NEXT update's bias corrections (torch computes them in fp64)
-    const int next = *step_ptr + 1;
-    step_ptr[1] = __float_as_int((float)(1.0 / (1.0 - pow((double)beta1, (double)next))));
-    step_ptr[2] = __float_as_int((float)sqrt(1.0 - pow((double)beta2, (double)next)));
-    step_ptr[3] = next;
-  }
-  if (scale_state) {
-    if (inf) {
-      scale_state[0] *= 0.5f;
-      scale_state[1] = 0.f;
-    } else {
-      scale_state[1] += 1.f;
-      if (scale_state[1] >= 2000.f) {
-        scale_state[0] *= 2.0f;
-        scale_state[1] = 0.f;
+  // ---- the last CTA to get here does the scalar bookkeeping (every CTA has read step/scale/found_inf by then): saves a launch
+  if (step_ptr) {
+    __syncthreads();                                        // every thread of this CTA has consumed the scalars (its stores depend on them)
+    if (threadIdx.x == 0) {                                 // no fence: the bookkeeping touches nothing the other CTAs write
+      if (atomicAdd(step_ptr + 4, 1) == (int)gridDim.x - 1) {
+        step_ptr[4] = 0;
+        adam_finish(step_ptr, scale_state, found_inf, tick, a.beta1, a.beta2);
       }
     }
   }
-  if (found_inf) *found_inf = 0;
 }
 
 }  // namespace nof
@@ -166,11 +182,13 @@ extern "C" int nof_adam_step(const NofAdamSeg* segs, int n_segs, float beta1, fl
   a.tile_begin[ADAM_MAX_SEGS] = (uint32_t)tiles;
   NOF_REQUIRE(tiles < 0x7fffffffull, "nof_adam_step: too many elements");
   cudaStream_t st = as_stream(stream);
+  unsigned long long* tk = reinterpret_cast<unsigned long long*>(tick);
   if (tiles > 0) {
-    adam_kernel<<<(uint32_t)tiles, ADAM_THREADS, 0, st>>>(a, step, scale_state, found_inf);
+    adam_kernel<<<(uint32_t)tiles, ADAM_THREADS, 0, st>>>(a, step, scale_state, found_inf, tk);
     int rc = check_launch("adam_kernel");
     if (rc) return rc;
+    if (step) return NOF_OK;                                 // the kernel's last CTA did the bookkeeping
   }
-  adam_finish_kernel<<<1, 1, 0, st>>>(step, scale_state, found_inf, reinterpret_cast<unsigned long long*>(tick), beta1, beta2);
+  adam_finish_kernel<<<1, 1, 0, st>>>(step, scale_state, found_inf, tk, beta1, beta2);
   return check_launch("adam_finish_kernel");
 }

@@ -245,33 +245,40 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, int
 
 // ------------------------------------------------------------------------------------------------ operand packing
 // fp32 packed parameters (nof_mlp_param_offsets order) -> the kernel's shared-memory image [W1 W2 W3 W4 W5 | biases]: fp16
-// weights in core-matrix order, zero padding, biases rounded through fp16 like torch autocast. One small CTA per step; the
+// weights in core-matrix order, zero padding, biases rounded through fp16 like torch autocast. One tiny kernel per step; the
 // 296 step CTAs then fetch the 21.5 KB image with one TMA bulk copy each instead of converting 9.6k weights each.
 template <int KE>
-__global__ void __launch_bounds__(1024) pack_mlp_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(256) pack_mlp_kernel(const StepArgs a) {
   const Plan sp = make_plan(KE);
   unsigned char* out = static_cast<unsigned char*>(a.wpack);      // image offset 0 == plan offset sp.w1 (== 0)
-  const int tid = threadIdx.x, E = a.E, V = a.V;
-  for (int i = tid; i < (sp.x0 - sp.w1) / 4; i += 1024) reinterpret_cast<uint32_t*>(out)[i] = 0u;
-  if (tid == 0) *reinterpret_cast<int*>(out + kWPackBytes - 16) = 0;                 // tile ticket of the step kernel
-  if (tid < 8) a.p.losses[tid] = 0.f;                                                // per-step results start from zero
-  if (a.p.grad_tf) for (int i = tid; i < a.p.F * 12; i += 1024) a.p.grad_tf[i] = 0.f;
-  __syncthreads();
+  const int gid = blockIdx.x * 256 + threadIdx.x;
+  if (gid == 0) *reinterpret_cast<int*>(out + kWPackBytes - 16) = 0;                 // tile ticket of the step kernel
+  if (gid < 8) a.p.losses[gid] = 0.f;                                                // per-step results start from zero
+  if (a.p.grad_tf) for (int i = gid; i < a.p.F * 12; i += gridDim.x * 256) a.p.grad_tf[i] = 0.f;
   const float* P = a.p.mlp;
-  auto put = [&](int base, int n, int k, int K, float v) { *reinterpret_cast<__half*>(out + base + cm_off(n, k, K)) = __float2half_rn(v); };
-  for (int i = tid; i < 64 * E; i += 1024) put(sp.w1, i / E, i % E, KE, P[a.po[0] + i]);
-  for (int i = tid; i < 16 * 64; i += 1024) put(sp.w2, i / 64, i % 64, 64, P[a.po[2] + i]);
-  const int K3 = V + 15;
-  for (int i = tid; i < 64 * K3; i += 1024) put(sp.w3, i / K3, i % K3, KC, P[a.po[4] + i]);
-  for (int i = tid; i < 64 * 64; i += 1024) put(sp.w4, i / 64, i % 64, 64, P[a.po[6] + i]);
-  for (int i = tid; i < 3 * 64; i += 1024) put(sp.w5, i / 64, i % 64, 64, P[a.po[8] + i]);
-  float* sB = reinterpret_cast<float*>(out + sp.bias);
-  auto rh = [](float v) { return __half2float(__float2half_rn(v)); };
-  for (int i = tid; i < 64; i += 1024) sB[i] = rh(P[a.po[1] + i]);
-  for (int i = tid; i < 16; i += 1024) sB[64 + i] = rh(P[a.po[3] + i]);
-  for (int i = tid; i < 64; i += 1024) sB[80 + i] = rh(P[a.po[5] + i]);
-  for (int i = tid; i < 64; i += 1024) sB[144 + i] = rh(P[a.po[7] + i]);
-  for (int i = tid; i < 3; i += 1024) sB[208 + i] = rh(P[a.po[9] + i]);
+  const int o = gid * 4;                                          // one 32-bit word of the image per thread: gather form, no zero pass
+  if (o < sp.bias) {
+    int base, rows, kreal, kpad, po;
+    if (o >= sp.w5) { base = sp.w5; rows = 3; kreal = 64; kpad = 64; po = a.po[8]; }
+    else if (o >= sp.w4) { base = sp.w4; rows = 64; kreal = 64; kpad = 64; po = a.po[6]; }
+    else if (o >= sp.w3) { base = sp.w3; rows = 64; kreal = a.V + 15; kpad = KC; po = a.po[4]; }
+    else if (o >= sp.w2) { base = sp.w2; rows = 16; kreal = 64; kpad = 64; po = a.po[2]; }
+    else { base = sp.w1; rows = 64; kreal = a.E; kpad = KE; po = a.po[0]; }
+    const int rel = o - base, rg = rel / (kpad * 16), rem = rel % (kpad * 16);
+    const int n = rg * 8 + (rem % 128) / 16, k = (rem / 128) * 8 + (rem % 16) / 2;          // inverse of cm_off
+    const float v0 = (n < rows && k < kreal) ? P[po + n * kreal + k] : 0.f;
+    const float v1 = (n < rows && k + 1 < kreal) ? P[po + n * kreal + k + 1] : 0.f;
+    *reinterpret_cast<uint32_t*>(out + o) = pack_h2(v0, v1);
+  } else if (o < sp.x0) {
+    const int j = (o - sp.bias) / 4;
+    float v = 0.f;
+    if (j < 64) v = P[a.po[1] + j];
+    else if (j < 80) v = P[a.po[3] + j - 64];
+    else if (j < 144) v = P[a.po[5] + j - 80];
+    else if (j < 208) v = P[a.po[7] + j - 144];
+    else if (j < 211) v = P[a.po[9] + j - 208];
+    *reinterpret_cast<float*>(out + o) = __half2float(__float2half_rn(v));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -846,7 +853,7 @@ static int launch_tc(const StepArgs& a, int blocks, cudaStream_t st) {
     once = true;
   }
   static_assert((size_t)(64 * KE * 2 + 16 * 64 * 2 + 64 * KC * 2 + 64 * 64 * 2 + 16 * 64 * 2 + 216 * 4 + 6 * 128 + 16) <= kWPackBytes, "wpack too small");
-  tc::pack_mlp_kernel<KE><<<1, 1024, 0, st>>>(a);
+  tc::pack_mlp_kernel<KE><<<(tc::make_plan(KE).x0 / 4 + 255) / 256, 256, 0, st>>>(a);
   tc::step_tc_kernel<KE><<<blocks, tc::NT, smem, st>>>(a);
   return check_launch("step_tc_kernel");
 }

@@ -203,7 +203,7 @@ class NerfRunner:
         self.param_groups_init = copy.deepcopy(self.optimizer.param_groups)
         dev = self.device
         z = lambda t: torch.zeros_like(t)
-        self._adam_step_buf = torch.zeros(4, dtype=torch.int32, device=dev)   # [0] step count, [1..3] library scratch (nof.h)
+        self._adam_step_buf = torch.zeros(8, dtype=torch.int32, device=dev)   # [0] step count, [1..7] library scratch (nof.h)
         self.adam_step_count = self._adam_step_buf[:1]
         # device-resident step state so that a captured CUDA graph of the step never needs new launch arguments:
         # learning rates (one per param group) and the RNG tick the sampler adds to its Philox offset

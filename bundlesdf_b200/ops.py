@@ -119,7 +119,10 @@ def fill_step_cfg(sb, cfg, trunc):
 
 
 def adam_step(segs, beta1, beta2, eps, step, scale_state=None, found_inf=None, tick=None):
-    """segs: list of dict(param, grad, exp_avg, exp_avg_sq, shadow_f16|None, lr). step: device int32 tensor [1]."""
+    """segs: list of dict(param, grad, exp_avg, exp_avg_sq, shadow_f16|None, lr). step: device int32 tensor [8] (include/nof.h:
+    [0] update count, the rest library scratch) or None."""
+    if step is not None and (step.numel() < 8 or step.dtype != torch.int32):
+        raise _lib.NofError('nof_adam_step: `step` must be a device int32[8] tensor (see include/nof.h)')
     lib = _lib.load()
     arr = (NofAdamSeg * len(segs))()
     for i, s in enumerate(segs):

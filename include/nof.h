@@ -205,8 +205,9 @@ typedef struct {
 /* Replaces optimizer.zero_grad() + GradScaler.unscale/inf-check/step/update + torch.optim.Adam.step
  * (nerf_runner.py:492-504, 756-761): exact dense Adam (betas, eps, no weight decay), single pass:
  * read g,m,v,p -> write p,m,v,(fp16 shadow) and zero g. Skips the update when *found_inf != 0.
- *   step: device int32[4]: [0] = number of Adam updates applied so far (incremented inside unless the step is skipped);
- *         [1..3] = scratch owned by the library (fp32 bias corrections cached for update [3]); zero-initialise all four.
+ *   step: device int32[8]: [0] = number of Adam updates applied so far (incremented inside unless the step is skipped);
+ *         [1..7] = scratch owned by the library (fp32 bias corrections cached for update [3], CTA completion counter [4]);
+ *         zero-initialise all eight. NULL = no step counter (bias corrections recomputed, bookkeeping in a second launch).
  *   scale_state: device float[2] = {loss_scale, growth_tracker} updated like GradScaler (init 65536,
  *                x2 every 2000 clean steps, x0.5 on inf) or NULL when amp is off.
  *   tick: optional device uint64 incremented on EVERY call (feeds NofMarchCfg.offset_ptr). */

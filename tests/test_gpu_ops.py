@@ -208,7 +208,7 @@ def test_adam_matches_torch_adam():
     dev = [dict(param=p.to(DEV), grad=torch.zeros(n, device=DEV), exp_avg=torch.zeros(n, device=DEV), exp_avg_sq=torch.zeros(n, device=DEV),
                 shadow_f16=(torch.zeros(n, device=DEV, dtype=torch.half) if i == 0 else None), lr=(0.01 if i < 2 else 0.003))
            for i, (p, n) in enumerate(zip(ps, sizes))]
-    step = torch.zeros(4, dtype=torch.int32, device=DEV)      # [0] count, [1..3] library scratch (include/nof.h)
+    step = torch.zeros(8, dtype=torch.int32, device=DEV)      # [0] count, [1..7] library scratch (include/nof.h)
     for it in range(5):
         grads = [torch.randn(n, generator=g) * (0.0 if (it == 2 and i == 1) else 1.0) for i, n in enumerate(sizes)]
         for r, gr in zip(ref, grads):
@@ -230,7 +230,7 @@ def test_adam_grad_scaler_skip_on_inf():
     n = 1000
     p = torch.ones(n, device=DEV)
     seg = [dict(param=p, grad=torch.full((n,), 65536.0, device=DEV), exp_avg=torch.zeros(n, device=DEV), exp_avg_sq=torch.zeros(n, device=DEV), lr=0.1)]
-    step = torch.zeros(4, dtype=torch.int32, device=DEV)      # [0] count, [1..3] library scratch (include/nof.h)
+    step = torch.zeros(8, dtype=torch.int32, device=DEV)      # [0] count, [1..7] library scratch (include/nof.h)
     scale = torch.tensor([65536.0, 0.0], device=DEV)
     inf = torch.ones(1, dtype=torch.int32, device=DEV)
     ops.adam_step(seg, 0.9, 0.999, 1e-15, step, scale, inf)
