@@ -13,7 +13,10 @@ namespace nof {
 
 constexpr int ADAM_MAX_SEGS = 8;
 constexpr int ADAM_THREADS = 256;
-constexpr int ADAM_UNR = 2;                                 // float4 groups per thread
+#ifndef NOF_ADAM_UNR
+#define NOF_ADAM_UNR 2
+#endif
+constexpr int ADAM_UNR = NOF_ADAM_UNR;                      // float4 groups per thread
 constexpr int ADAM_TILE = ADAM_THREADS * ADAM_UNR * 4;      // 2048 elements per CTA
 
 struct AdamArgs {
@@ -23,6 +26,17 @@ struct AdamArgs {
   float beta1, beta2, eps;
 };
 
+// torch computes the bias corrections in fp64; kept out of line so that the streaming kernel's register count stays at 4 CTAs/SM
+#ifdef NOF_ADAM_INLINE_COLD
+static __device__ __forceinline__ void bias_corrections_cold(
+#else
+static __device__ __noinline__ void bias_corrections_cold(
+#endif
+    float beta1, float beta2, int step, float* out) {
+  out[0] = (float)(1.0 / (1.0 - pow((double)beta1, (double)step)));
+  out[1] = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+}
+
 // GradScaler.update() (growth_factor 2, backoff 0.5, growth_interval 2000) + step counter + RNG tick + flag reset.
 __device__ __forceinline__ void adam_finish(int32_t* step_ptr, float* scale_state, int32_t* found_inf, unsigned long long* tick, float beta1,
                                             float beta2) {
@@ -31,8 +45,10 @@ __device__ __forceinline__ void adam_finish(int32_t* step_ptr, float* scale_stat
   if (!inf && step_ptr) *step_ptr += 1;
   if (step_ptr) {                                           // cache the NEXT update's bias corrections (torch computes them in fp64)
     const int next = *step_ptr + 1;
-    step_ptr[1] = __float_as_int((float)(1.0 / (1.0 - pow((double)beta1, (double)next))));
-    step_ptr[2] = __float_as_int((float)sqrt(1.0 - pow((double)beta2, (double)next)));
+    float bc[2];
+    bias_corrections_cold(beta1, beta2, next, bc);
+    step_ptr[1] = __float_as_int(bc[0]);
+    step_ptr[2] = __float_as_int(bc[1]);
     step_ptr[3] = next;
   }
   if (scale_state) {
@@ -55,7 +71,10 @@ __global__ void adam_finish_kernel(int32_t* step_ptr, float* scale_state, int32_
   adam_finish(step_ptr, scale_state, found_inf, tick, beta1, beta2);
 }
 
-__global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a, int32_t* step_ptr, float* scale_state, int32_t* found_inf,
+#ifndef NOF_ADAM_MINB
+#define NOF_ADAM_MINB 4
+#endif
+__global__ void __launch_bounds__(ADAM_THREADS, NOF_ADAM_MINB) adam_kernel(const AdamArgs a, int32_t* step_ptr, float* scale_state, int32_t* found_inf,
                                                             unsigned long long* tick) {
   const uint32_t tile = blockIdx.x;
   int si = 0;
@@ -94,10 +113,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a, in
   const float lr = sg.lr_ptr ? *sg.lr_ptr : sg.lr;
   if (!cached) {                                            // CTA-uniform
     __shared__ float s_bc[2];
-    if (threadIdx.x == 0) {
-      s_bc[0] = (float)(1.0 / (1.0 - pow((double)a.beta1, (double)step)));
-      s_bc[1] = (float)sqrt(1.0 - pow((double)a.beta2, (double)step));
-    }
+    if (threadIdx.x == 0) bias_corrections_cold(a.beta1, a.beta2, step, s_bc);
     __syncthreads();
     inv_bc1 = s_bc[0];
     sqrt_bc2 = s_bc[1];
