@@ -74,32 +74,37 @@ __global__ void interval_walk_kernel(const float* __restrict__ z_in_out, const f
 }
 
 // ------------------------------------------------------------------------------------------------
-// torch.linspace(0,1,S) as its CUDA kernel evaluates it (step=(end-start)/(steps-1); lower half start+step*i,
-// upper half end-step*(steps-i-1), each contracted to one FMA).
-__device__ __forceinline__ float linspace01(int i, int S) {
-  if (S == 1) return 0.f;
-  const float step = __fdiv_rn(1.0f, (float)(S - 1));
-  return (i < S / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(S - i - 1), 1.0f);
-}
+constexpr int MARCH_WARPS = 8;
 
+// torch.linspace(0,1,S) as its CUDA kernel evaluates it (step=(end-start)/(steps-1); lower half start+step*i, upper half
+// end-step*(steps-i-1), each contracted to one FMA); the division is hoisted out of the per-sample code.
+struct Lin { float step; int S; };
+__device__ __forceinline__ float lin_at(const Lin& L, int i) {
+  if (L.S == 1) return 0.f;
+  return (i < L.S / 2) ? __fmul_rn(L.step, (float)i) : __fmaf_rn(-L.step, (float)(L.S - i - 1), 1.0f);
+}
 // sample_rays_uniform (nerf_runner.py:67-87) for one (ray, sample): stratified value in [near, far].
-__device__ __forceinline__ float stratified(int i, int S, float nearv, float farv, bool perturb, float u) {
+__device__ __forceinline__ float strat_one(const Lin& L, int i, float nearv, float farv, bool perturb, float u) {
   auto zlin = [&](int j) {
-    const float t = linspace01(j, S);
+    const float t = lin_at(L, j);
     return __fadd_rn(__fmul_rn(nearv, __fsub_rn(1.f, t)), __fmul_rn(farv, t));
   };
   float z = zlin(i);
   if (perturb) {
     const float lower = (i == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, zlin(i - 1)));
-    const float upper = (i == S - 1) ? z : __fmul_rn(0.5f, __fadd_rn(zlin(i + 1), z));
+    const float upper = (i == L.S - 1) ? z : __fmul_rn(0.5f, __fadd_rn(zlin(i + 1), z));
     z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u));
     z = fminf(fmaxf(z, nearv), farv);
   }
   return z;
 }
 
-constexpr int MARCH_WARPS = 8;
-
+// One warp per ray. The voxel DDA is a sequential walk on lane 0 (sharing one instruction stream between 8 rays on 8 lanes of
+// one warp was tried: the walk's dependent chain, not issue slots, is what the kernel waits for, 19.7 -> 24.8 us), so the step is
+// kept short: the exit time of each axis is cached and recomputed only for the axis that moved (a pure function of ix[a], hence
+// bit-identical to recomputing all three), and the reference's `(double)|dt| < 1e-4` is the float test `|dt| <= 1e-4f` (the
+// float nearest to 1e-4 lies below it, the next one above). Samples: all 32 lanes, a lane owns 4 consecutive samples (one
+// Philox call, one 16-byte store).
 __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg cfg, const float* __restrict__ rays,
                                                                      const float* __restrict__ tf,
                                                                      const uint32_t* __restrict__ occ_bits,
@@ -110,40 +115,39 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg
   extern __shared__ uint32_t smem_u32[];
   const int n = 1 << cfg.level;
   const int occ_words = (n * n * n + 31) / 32;
+  const int I = cfg.I_max;
   uint32_t* s_occ = smem_u32;
-  float* s_io_all = reinterpret_cast<float*>(smem_u32 + occ_words);
+  float* s_io_t = reinterpret_cast<float*>(smem_u32 + occ_words);       // [MARCH_WARPS][I][2] travel-time intervals per ray
+  float* s_io_z = s_io_t + (size_t)MARCH_WARPS * I * 2;                 // [MARCH_WARPS][I][2] z intervals (scaled, clipped)
+  int* s_count = reinterpret_cast<int*>(s_io_z + (size_t)MARCH_WARPS * I * 2);   // [MARCH_WARPS] intervals, [MARCH_WARPS] overflow
   for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s_occ[i] = occ_bits[i];
-  __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int I = cfg.I_max;
-  float* io_t = s_io_all + (size_t)warp * I * 4;       // travel-time intervals
-  float* io_z = io_t + (size_t)I * 2;                  // z intervals (scaled, clipped)
   const int S = cfg.S_occ + cfg.S_depth;
   if (cfg.offset_ptr) cfg.offset += *cfg.offset_ptr;
+  const Lin lin_occ = {cfg.S_occ > 1 ? __fdiv_rn(1.0f, (float)(cfg.S_occ - 1)) : 0.f, cfg.S_occ};
+  const Lin lin_d = {cfg.S_depth > 1 ? __fdiv_rn(1.0f, (float)(cfg.S_depth - 1)) : 0.f, cfg.S_depth};
 
+  __syncthreads();                                     // bitmask staged
   for (int r = blockIdx.x * MARCH_WARPS + warp; r < cfg.N; r += gridDim.x * MARCH_WARPS) {
-    const float* row = rays + (size_t)r * cfg.ray_dim;
-    const float dx = row[0], dy = row[1], dz = row[2];
-    const float depth = row[6];
-    const int frame = (int)row[8];
-    const float* T = tf + (size_t)frame * 12;
-    // unit camera-frame direction, world origin and world direction (nerf_runner.py:1045-1057)
-    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-    const float ux = __fdiv_rn(dx, nrm), uy = __fdiv_rn(dy, nrm), uz = __fdiv_rn(dz, nrm);
-    float o[3], d[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      o[a] = T[a * 4 + 3];
-      d[a] = __fadd_rn(__fadd_rn(__fmul_rn(T[a * 4 + 0], ux), __fmul_rn(T[a * 4 + 1], uy)), __fmul_rn(T[a * 4 + 2], uz));
-    }
-    int count = 0;
-    bool overflow = false;
+    // ================= phase 1: DDA (replaces kaolin unbatched_raytrace; packing rule of common.cu:137-148 applied on the fly)
     if (lane == 0) {
-      // ---- voxel DDA (replaces kaolin unbatched_raytrace; packing rule of common.cu:137-148 applied on the fly)
-      float inv[3];
+      const float* row = rays + (size_t)r * cfg.ray_dim;
+      const float dx = row[0], dy = row[1], dz = row[2];
+      const float* T = tf + (size_t)((int)row[8]) * 12;
+      // unit camera-frame direction, world origin and world direction (nerf_runner.py:1045-1057)
+      const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+      const float ux = __fdiv_rn(dx, nrm), uy = __fdiv_rn(dy, nrm), uz = __fdiv_rn(dz, nrm);
+      float o[3], d[3], inv[3];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) inv[a] = __fdiv_rn(1.0f, d[a]);
+      for (int a = 0; a < 3; ++a) {
+        o[a] = T[a * 4 + 3];
+        d[a] = __fadd_rn(__fadd_rn(__fmul_rn(T[a * 4 + 0], ux), __fmul_rn(T[a * 4 + 1], uy)), __fmul_rn(T[a * 4 + 2], uz));
+        inv[a] = __fdiv_rn(1.0f, d[a]);
+      }
+      float* io_t = s_io_t + (size_t)warp * I * 2;
+      int count = 0;
+      bool overflow = false;
       float t0 = 0.f, t1 = __int_as_float(0x7f800000);
       bool hit = true;
 #pragma unroll
@@ -160,33 +164,34 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg
       if (hit && t0 < t1) {
         const float cell = __fdiv_rn(2.0f, (float)n);
         int ix[3], step[3];
+        float tnext[3];                                 // exit time through the next plane of each axis: a pure function of ix[a]
+        auto plane_t = [&](int a) {
+          const float plane = __fsub_rn(__fmul_rn((float)(ix[a] + (step[a] > 0 ? 1 : 0)), cell), 1.0f);
+          return __fmul_rn(__fsub_rn(plane, o[a]), inv[a]);
+        };
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const float p = __fadd_rn(o[a], __fmul_rn(t0, d[a]));
-          int c = (int)floorf(__fdiv_rn(__fadd_rn(p, 1.0f), cell));
+          const int c = (int)floorf(__fdiv_rn(__fadd_rn(p, 1.0f), cell));
           ix[a] = min(max(c, 0), n - 1);
           step[a] = d[a] > 0.f ? 1 : (d[a] < 0.f ? -1 : 0);
+          tnext[a] = step[a] != 0 ? plane_t(a) : __int_as_float(0x7f800000);
         }
         float t_in = t0;
-        bool stopped = false;                   // the packing rule's `break` (t_in==0 || t_out==0)
+        bool stopped = false;                           // the packing rule's `break` (t_in==0 || t_out==0)
         for (int guard = 0; guard < 3 * n + 3; ++guard) {
           float t_out = __int_as_float(0x7f800000);
           int ax = -1;
 #pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            if (step[a] != 0) {
-              const float plane = __fsub_rn(__fmul_rn((float)(ix[a] + (step[a] > 0 ? 1 : 0)), cell), 1.0f);
-              const float ta = __fmul_rn(__fsub_rn(plane, o[a]), inv[a]);
-              if (ta < t_out) { t_out = ta; ax = a; }
-            }
-          }
+          for (int a = 0; a < 3; ++a)
+            if (step[a] != 0 && tnext[a] < t_out) { t_out = tnext[a]; ax = a; }
           if (ax < 0) break;
           t_out = fminf(t_out, t1);
           const int cid = (ix[0] * n + ix[1]) * n + ix[2];
           if (!stopped && ((s_occ[cid >> 5] >> (cid & 31)) & 1u)) {
             if (t_in == 0.f || t_out == 0.f) {
               stopped = true;
-            } else if (!(t_in > t_out) && !((double)fabsf(__fsub_rn(t_out, t_in)) < 1e-4)) {
+            } else if (!(t_in > t_out) && !(fabsf(__fsub_rn(t_out, t_in)) <= 1e-4f)) {
               if (count < I) {
                 io_t[2 * count] = t_in;
                 io_t[2 * count + 1] = t_out;
@@ -196,14 +201,28 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg
               }
             }
           }
-          ix[ax] += step[ax];
-          if (ix[ax] < 0 || ix[ax] >= n || t_out >= t1) break;
+          if (ax == 0) { ix[0] += step[0]; tnext[0] = plane_t(0); }
+          else if (ax == 1) { ix[1] += step[1]; tnext[1] = plane_t(1); }
+          else { ix[2] += step[2]; tnext[2] = plane_t(2); }
+          const int moved = ax == 0 ? ix[0] : (ax == 1 ? ix[1] : ix[2]);
+          if (moved < 0 || moved >= n || t_out >= t1) break;
           t_in = t_out;
         }
       }
+      s_count[warp] = count;
+      s_count[MARCH_WARPS + warp] = overflow ? 1 : 0;
     }
-    count = __shfl_sync(0xffffffffu, count, 0);
     __syncwarp();
+    // ================= phase 2: samples
+    const float* row = rays + (size_t)r * cfg.ray_dim;
+    const float dx = row[0], dy = row[1], dz = row[2];
+    const float depth = row[6];
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float uz = __fdiv_rn(dz, nrm);
+    float* io_t = s_io_t + (size_t)warp * I * 2;
+    float* io_z = s_io_z + (size_t)warp * I * 2;
+    const int count = s_count[warp];
+    const bool overflow = s_count[MARCH_WARPS + warp] != 0;
     // ---- z intervals: t -> z (nerf_runner.py:987-990), clip to depth+trunc for valid-depth rays (:992-999)
     const float absz = fabsf(uz);
     const bool valid_depth = (depth >= cfg.near_sc) && (depth <= cfg.far_sc);
@@ -228,52 +247,54 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg
       io_z[2 * k + 1] = b;
     }
     __syncwarp();
-    // total occupied length, summed front to back (every lane redundantly; I is small)
+    // total occupied length, summed front to back (every lane redundantly); entries beyond `count` are exact zeros
     float total = 0.f;
-    for (int k = 0; k < I; ++k) total = __fadd_rn(total, __fsub_rn(io_z[2 * k + 1], io_z[2 * k]));
+    for (int k = 0; k < count; ++k) total = __fadd_rn(total, __fsub_rn(io_z[2 * k + 1], io_z[2 * k]));
+    float total2 = 0.f;
+    if (cfg.S_depth > 0 && !valid_depth)
+      for (int k = 0; k < count; ++k) total2 = __fadd_rn(total2, __fsub_rn(io_t[2 * k + 1], io_t[2 * k]));
+    const float nd = __fsub_rn(depth, cfg.trunc);
+    const float fd = __fadd_rn(depth, __fmul_rn(cfg.trunc, cfg.neg_trunc_ratio));
     bool err = false;
     float* zrow = z_vals + (size_t)r * S;
     const bool has_any = io_z[0] != 0.f;       // common.cu:54: rays without intervals keep z = 0
-    for (int s = lane; s < cfg.S_occ; s += 32) {
-      float u = 0.f;
+    const bool has_any_t = io_t[0] != 0.f;
+    const bool vec_ok = (S & 3) == 0 && (reinterpret_cast<uintptr_t>(z_vals) & 15u) == 0;
+    for (int s0 = 4 * lane; s0 < S; s0 += 128) {
+      float u4[4] = {0.f, 0.f, 0.f, 0.f};
       if (cfg.perturb) {
-        if (t_rand) u = t_rand[(size_t)r * S + s];
-        else {
-          uint4 rnd = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)(s >> 2), (uint32_t)cfg.offset, (uint32_t)(cfg.offset >> 32)),
-                                    make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32)));
-          const uint32_t w = (s & 3) == 0 ? rnd.x : (s & 3) == 1 ? rnd.y : (s & 3) == 2 ? rnd.z : rnd.w;
-          u = u32_to_unit(w);
+        if (t_rand) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (s0 + j < S) u4[j] = t_rand[(size_t)r * S + s0 + j];
+        } else {
+          const uint4 rnd = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)(s0 >> 2), (uint32_t)cfg.offset, (uint32_t)(cfg.offset >> 32)),
+                                          make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32)));
+          u4[0] = u32_to_unit(rnd.x); u4[1] = u32_to_unit(rnd.y); u4[2] = u32_to_unit(rnd.z); u4[3] = u32_to_unit(rnd.w);
         }
       }
-      const float zc = stratified(s, cfg.S_occ, 0.f, total, cfg.perturb != 0, u);
-      zrow[s] = has_any ? walk_intervals(io_z, I, zc, &err) : 0.f;
-    }
-    // ---- around-depth samples (nerf_runner.py:1063-1081)
-    if (cfg.S_depth > 0) {
-      float total2 = 0.f;
-      if (!valid_depth) for (int k = 0; k < I; ++k) total2 = __fadd_rn(total2, __fsub_rn(io_t[2 * k + 1], io_t[2 * k]));
-      const float nd = __fsub_rn(depth, cfg.trunc);
-      const float fd = __fadd_rn(depth, __fmul_rn(cfg.trunc, cfg.neg_trunc_ratio));
-      for (int j = lane; j < cfg.S_depth; j += 32) {
-        const int s = cfg.S_occ + j;
-        float u = 0.f;
-        if (cfg.perturb) {
-          if (t_rand) u = t_rand[(size_t)r * S + s];
-          else {
-            uint4 rnd = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)(s >> 2), (uint32_t)cfg.offset, (uint32_t)(cfg.offset >> 32)),
-                                      make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32)));
-            const uint32_t w = (s & 3) == 0 ? rnd.x : (s & 3) == 1 ? rnd.y : (s & 3) == 2 ? rnd.z : rnd.w;
-            u = u32_to_unit(w);
+      float z4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int s = s0 + j;
+        if (s >= S) break;
+        if (s < cfg.S_occ) {                            // stratified over the occupied length (nerf_runner.py:979-1011)
+          const float zc = strat_one(lin_occ, s, 0.f, total, cfg.perturb != 0, u4[j]);
+          z4[j] = has_any ? walk_intervals(io_z, I, zc, &err) : 0.f;
+        } else {                                        // around-depth samples (nerf_runner.py:1063-1081)
+          const int jj = s - cfg.S_occ;
+          if (valid_depth) {
+            z4[j] = strat_one(lin_d, jj, nd, fd, cfg.perturb != 0, u4[j]);
+          } else {                                      // second occupied-voxel sampling, unclipped (:1074-1076)
+            const float zc = strat_one(lin_d, jj, 0.f, total2, cfg.perturb != 0, u4[j]);
+            z4[j] = has_any_t ? walk_intervals(io_t, I, zc, &err) : 0.f;
           }
         }
-        float z;
-        if (valid_depth) {
-          z = stratified(j, cfg.S_depth, nd, fd, cfg.perturb != 0, u);
-        } else {                                 // second occupied-voxel sampling, unclipped (:1074-1076)
-          const float zc = stratified(j, cfg.S_depth, 0.f, total2, cfg.perturb != 0, u);
-          z = (io_t[0] != 0.f) ? walk_intervals(io_t, I, zc, &err) : 0.f;
-        }
-        zrow[s] = z;
+      }
+      if (vec_ok) {
+        *reinterpret_cast<float4*>(zrow + s0) = make_float4(z4[0], z4[1], z4[2], z4[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (s0 + j < S) zrow[s0 + j] = z4[j];
       }
     }
     if ((err || (lane == 0 && overflow)) && err_flag) atomicExch(err_flag, 1);
@@ -333,7 +354,7 @@ extern "C" int nof_ray_march(const NofMarchCfg* cfg, const float* rays, const fl
   NOF_REQUIRE(cfg->S_occ >= 1 && cfg->S_depth >= 0, "nof_ray_march: bad sample counts");
   if (cfg->N == 0) return NOF_OK;
   const int n = 1 << cfg->level;
-  const size_t smem = (size_t)((n * n * n + 31) / 32) * 4 + (size_t)MARCH_WARPS * cfg->I_max * 4 * sizeof(float);
+  const size_t smem = (size_t)((n * n * n + 31) / 32) * 4 + (size_t)MARCH_WARPS * cfg->I_max * 4 * sizeof(float) + 2 * MARCH_WARPS * sizeof(int);
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
     cudaFuncSetAttribute(ray_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
