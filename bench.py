@@ -57,46 +57,72 @@ def algorithmic_bytes(c):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line). NVML (the library behind
+    nvidia-smi, ~50 us per query) every 2 ms, so that even a 60 ms region gets dozens of samples; falls back to spawning
+    `nvidia-smi --query-gpu=clocks.sm,...` (100+ ms per sample) when pynvml is not importable."""
+
+    REASONS = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'), (0x4, 'sw_power_cap'))
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.rows, self._stop_evt, self.error, self.source = index, [], threading.Event(), None, None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:                                            # honour CUDA_VISIBLE_DEVICES remapping: look the device up by UUID
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml, self._h, self.source = pynvml, h, 'nvml'
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:
+            self.error = repr(e)[:200]
+
+    def _sample_nvml(self):
+        nv, h = self._nvml, self._h
+        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        self.rows.append((sm, self.sm_max, mask))
+
+    def _sample_smi(self):
+        r = subprocess.run(['nvidia-smi', f'--id={self.index}', '--query-gpu=clocks.sm,clocks.max.sm,clocks_throttle_reasons.active',
+                            '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+        f = [x.strip() for x in r.stdout.strip().split(',')]
+        if r.returncode == 0 and len(f) >= 2 and f[0].replace('.', '').isdigit():
+            mask = int(f[2], 16) if len(f) > 2 and f[2].lower().startswith('0x') else 0
+            self.rows.append((float(f[0]), float(f[1]), mask))
+        else:
+            self.error = (r.stdout.strip() or r.stderr.strip())[:200]
 
     def run(self):
-        qs = ['clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap',
-              'clocks.sm,clocks.max.sm,clocks_throttle_reasons.hw_slowdown,clocks_throttle_reasons.hw_thermal_slowdown,'
-              'clocks_throttle_reasons.sw_thermal_slowdown,clocks_throttle_reasons.sw_power_cap',
-              'clocks.sm,clocks.max.sm']
-        qi = 0
-        self.error = None
+        self.source = self.source or 'nvidia-smi'
         while not self._stop_evt.is_set():
             try:
-                r = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={qs[qi]}', '--format=csv,noheader,nounits'],
-                                   capture_output=True, text=True, timeout=5)
-                out = r.stdout.strip()
-                if r.returncode == 0 and out and 'not a valid' not in out.lower() and out[0].isdigit():
-                    self.rows.append([x.strip() for x in out.split(',')])
-                elif qi + 1 < len(qs):
-                    self.error = (out or r.stderr.strip())[:200]
-                    qi += 1
-                    continue
+                if self._nvml is not None:
+                    self._sample_nvml()
                 else:
-                    self.error = (out or r.stderr.strip())[:200]
+                    self._sample_smi()
             except Exception as e:
                 self.error = repr(e)[:200]
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.002 if self._nvml is not None else 0.2)
 
     def summary(self):
         self._stop_evt.set()
+        self.join(timeout=6)
         if not self.rows:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable'], 'error': getattr(self, 'error', None)}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in self.rows)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.rows[0][1]) if self.rows[0][1].replace('.', '').isdigit() else None,
-                'reasons': reasons, 'samples': len(self.rows)}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable'], 'error': self.error}
+        sm = sorted(r[0] for r in self.rows)
+        mask = 0
+        for r in self.rows:
+            mask |= r[2]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': self.rows[0][1], 'reasons': [n for bit, n in self.REASONS if mask & bit],
+                'samples': len(self.rows), 'source': self.source}
 
 
 def build_runner(c, seed, device, eager=False):
