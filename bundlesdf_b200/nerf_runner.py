@@ -573,27 +573,34 @@ class NerfRunner:
 
     @torch.no_grad()
     def extract_mesh(self, level=None, voxel_size=0.003, isolevel=0.0, return_sigma=False):
-        """nerf_runner.py:1351-1409: SDF on a dense grid (only inside occupied cells), then marching cubes. The SDF sweep runs on
-        the native query kernel; marching cubes uses scikit-image when available (it is not in the build image: then only
-        `return_sigma=True` callers get a result and mesh is None)."""
+        """nerf_runner.py:1351-1409: SDF on a dense grid (only inside occupied cells), then the iso-surface. Both steps run on the
+        GPU: the SDF sweep on the native query kernel, the surface on nof_marching_tets (the reference calls
+        skimage's Lewiner marching cubes on the host: same surface up to the triangulation inside a cell, not the same triangles).
+        Returns a `trimesh.Trimesh` when trimesh is installed (like the reference), else `bundlesdf_b200.mesh.TriMesh`."""
         vs = voxel_size * self.cfg['sc_factor']
         bounds = np.array(self.cfg['bounding_box']).reshape(2, 3)
         axes = [np.arange(bounds[0, i] + 0.5 * vs, bounds[1, i], vs) for i in range(3)]
-        Nx = len(axes[0])
+        dims = [len(a) for a in axes]
         grid = torch.tensor(np.stack(np.meshgrid(*axes, indexing='ij'), -1).astype(np.float32).reshape(-1, 3)).to(self.device)
         valid = self.octree_m.get_center_ids(grid) >= 0 if self.octree_m is not None else torch.ones(len(grid), dtype=torch.bool, device=self.device)
-        sigma = torch.ones(len(grid), device=self.device)
+        sigma_dev = torch.ones(len(grid), device=self.device)
         if valid.any():
-            sigma[valid] = ops.query_sdf(self._model_args(), grid[valid].contiguous())
-        sigma = sigma.reshape(Nx, Nx, Nx).cpu().numpy()
+            sigma_dev[valid] = ops.query_sdf(self._model_args(), grid[valid].contiguous())
+        sigma_dev = sigma_dev.reshape(*dims)
+        sigma = sigma_dev.cpu().numpy()
         mesh = None
         try:
-            from skimage import measure
-            import trimesh
-            verts, tris, _, _ = measure.marching_cubes(sigma, isolevel)
+            verts, tris = ops.marching_tets(sigma_dev, isolevel)
+            if len(tris) == 0:
+                raise RuntimeError('no surface at this isolevel')            # skimage raises here too -> reference returns None
             step = np.array([a[-1] - a[0] for a in axes]) / np.array([len(a) - 1 for a in axes])
-            verts = step.reshape(1, 3) * verts + np.array([a[0] for a in axes]).reshape(1, 3)
-            mesh = trimesh.Trimesh(verts, tris, process=False)
+            verts = step.reshape(1, 3) * verts.cpu().numpy().astype(np.float64) + np.array([a[0] for a in axes]).reshape(1, 3)
+            try:
+                import trimesh
+                mesh = trimesh.Trimesh(verts, tris.cpu().numpy(), process=False)
+            except ImportError:
+                from .mesh import TriMesh
+                mesh = TriMesh(verts, tris.cpu().numpy())
         except Exception as e:                      # same policy as the reference (:1390-1394): log and return None
             logging.info(f'ERROR Marching Cubes {e}')
         if return_sigma:

@@ -139,3 +139,29 @@ def query_sdf(sb, x, out=None):
     sdf = out if out is not None else torch.empty(P, device=x.device, dtype=torch.float32)
     _lib.check(lib.nof_query_sdf(C.byref(sb.s), _lib.ptr(x), _lib.ptr(sdf), P, _lib.stream()), 'nof_query_sdf')
     return sdf
+
+
+def marching_tets(field, iso=0.0):
+    """Iso-surface of a dense [nx,ny,nz] fp32 CUDA grid (include/nof.h nof_marching_tets_*). Returns (vertices [V,3] fp32 in
+    grid-index coordinates, faces [F,3] int64), vertices welded, triangles facing increasing field values."""
+    lib = _lib.load()
+    field = field.contiguous().float()
+    nx, ny, nz = (int(x) for x in field.shape)
+    cells = (nx - 1) * (ny - 1) * (nz - 1)
+    counts = torch.empty(cells, dtype=torch.int32, device=field.device)
+    _lib.check(lib.nof_marching_tets_count(_lib.ptr(field), nx, ny, nz, float(iso), _lib.ptr(counts), _lib.stream()), 'nof_marching_tets_count')
+    csum = torch.cumsum(counts, 0, dtype=torch.int64)
+    T = int(csum[-1].item()) if cells > 0 else 0
+    if T == 0:
+        return torch.zeros(0, 3, device=field.device), torch.zeros(0, 3, dtype=torch.int64, device=field.device)
+    offsets = (csum - counts).contiguous()
+    verts = torch.empty(T, 3, 3, device=field.device, dtype=torch.float32)
+    keys = torch.empty(T, 3, dtype=torch.int64, device=field.device)
+    _lib.check(lib.nof_marching_tets_emit(_lib.ptr(field), nx, ny, nz, float(iso), _lib.ptr(offsets), _lib.ptr(verts), _lib.ptr(keys),
+                                          _lib.stream()), 'nof_marching_tets_emit')
+    uniq, inv = torch.unique(keys.reshape(-1), return_inverse=True)
+    vertices = torch.empty(len(uniq), 3, device=field.device, dtype=torch.float32)
+    vertices[inv] = verts.reshape(-1, 3)                     # equal keys carry bit-identical positions
+    faces = inv.reshape(-1, 3)
+    keep = (faces[:, 0] != faces[:, 1]) & (faces[:, 1] != faces[:, 2]) & (faces[:, 0] != faces[:, 2])
+    return vertices, faces[keep].contiguous()

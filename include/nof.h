@@ -218,6 +218,16 @@ int nof_adam_step(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, 
  * NeRFSmall.forward_sdf nerf_helpers.py:296-302): x [P,3] in [-1,1] (clipped inside) -> sdf [P]. */
 int nof_query_sdf(const NofStep* model, const float* x, float* sdf, int64_t P, nof_stream_t stream);
 
+/* Iso-surface of a dense scalar grid for NerfRunner.extract_mesh (nerf_runner.py:1387-1404 calls skimage.measure.marching_cubes
+ * on the host). Marching tetrahedra over the Kuhn split of each cell (closed 2-manifold, no case tables); two passes:
+ *   count: field [nx,ny,nz] (C order) -> counts [(nx-1)(ny-1)(nz-1)] triangles per cell (int32);
+ *   emit:  offsets = exclusive prefix sum of counts (int64) -> verts [T,3,3] (grid-index coordinates, fp32) and
+ *          keys [T,3] (int64: id of the grid edge the vertex lies on = lower end-point index * 8 + direction code); equal keys
+ *          carry bit-identical positions, so vertices are welded by `unique(keys)`. Triangles face increasing field values. */
+int nof_marching_tets_count(const float* field, int nx, int ny, int nz, float iso, int32_t* counts, nof_stream_t stream);
+int nof_marching_tets_emit(const float* field, int nx, int ny, int nz, float iso, const int64_t* offsets, float* verts,
+                           int64_t* keys, nof_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

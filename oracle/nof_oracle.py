@@ -684,3 +684,106 @@ def adam_update(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-15):
 def lr_at(cfg, lr0, global_step):
     """schedule_lr, nerf_runner.py:579-583."""
     return lr0 * (cfg['decay_rate'] ** (float(global_step) / (cfg['n_step'] + 1)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Iso-surface extraction (checker for nof_marching_tets_*, include/nof.h; downstream of the path: extract_mesh,
+# nerf_runner.py:1387-1404). Same algorithm in numpy: Kuhn split of each cell into 6 tetrahedra, one vertex per crossed grid
+# edge interpolated from the lower-index end point (fp32, same operation order), triangles oriented towards increasing values.
+MT_CORNER = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], np.int64)
+MT_TET = np.array([[0, 5, 1, 6], [0, 1, 2, 6], [0, 2, 3, 6], [0, 3, 7, 6], [0, 7, 4, 6], [0, 4, 5, 6]], np.int64)
+
+
+def marching_tets_np(field, iso=0.0):
+    """field [nx,ny,nz] float32 -> (verts [T,3,3] float32 grid coordinates, keys [T,3] int64), cell-major / tet order."""
+    f = np.asarray(field, np.float32)
+    nx, ny, nz = f.shape
+    iso = np.float32(iso)
+    ci, cj, ck = np.meshgrid(np.arange(nx - 1), np.arange(ny - 1), np.arange(nz - 1), indexing='ij')
+    base = np.stack([ci.ravel(), cj.ravel(), ck.ravel()], -1)                       # [cells,3]
+    verts_out, keys_out, order = [], [], []
+
+    def edge_vertex(cells, qa, qb):
+        pa = base[cells] + MT_CORNER[qa]
+        pb = base[cells] + MT_CORNER[qb]
+        ia = (pa[:, 0] * ny + pa[:, 1]) * nz + pa[:, 2]
+        ib = (pb[:, 0] * ny + pb[:, 1]) * nz + pb[:, 2]
+        a_lo = ia < ib
+        lo = np.where(a_lo[:, None], pa, pb)
+        hi = np.where(a_lo[:, None], pb, pa)
+        vl = f[lo[:, 0], lo[:, 1], lo[:, 2]]
+        vh = f[hi[:, 0], hi[:, 1], hi[:, 2]]
+        t = ((iso - vl).astype(np.float32) / (vh - vl).astype(np.float32)).astype(np.float32)
+        d = (hi - lo).astype(np.float32)
+        # fmaf(t, d, lo) with d in {0,1}: t*d is exact, so one rounding like the fused form
+        p = (t[:, None].astype(np.float64) * d.astype(np.float64) + lo.astype(np.float64)).astype(np.float32)
+        key = np.where(a_lo, ia, ib) * 8 + ((hi - lo) @ np.array([4, 2, 1]))
+        return p, key
+
+    for t in range(6):
+        q = MT_TET[t]
+        pc = base[:, None, :] + MT_CORNER[q][None]                                  # [cells,4,3]
+        v = f[pc[..., 0], pc[..., 1], pc[..., 2]]                                   # [cells,4]
+        inside = v < iso
+        n_in = inside.sum(1)
+        for cells in [np.nonzero(n_in == 1)[0], np.nonzero(n_in == 3)[0], np.nonzero(n_in == 2)[0]]:
+            if len(cells) == 0:
+                continue
+            ins = inside[cells]
+            # positions (0..3) of inside / outside vertices, ascending like the kernel's loop
+            idx = np.argsort(~ins, axis=1, kind='stable')                           # inside first, each group ascending
+            ni = int(ins[0].sum())
+            pin, pout = idx[:, :ni], idx[:, ni:]
+            # winding from the tetrahedron's orientation (exact integer determinant), not from the triangle's geometry
+            if ni == 1:
+                L4 = np.concatenate([pin[:, :1], pout[:, :3]], 1)
+            elif ni == 3:
+                L4 = np.concatenate([pout[:, :1], pin[:, :3]], 1)
+            else:
+                L4 = np.concatenate([pin[:, :2], pout[:, :2]], 1)
+            cpos = MT_CORNER[q]                                                     # [4,3] integer corner coordinates
+            P = cpos[L4]                                                            # [cells,4,3]
+            D = np.linalg.det((P[:, 1:] - P[:, :1]).astype(np.float64))
+            flip = (D > 0.5) if ni == 3 else (D < -0.5)
+
+            def ev(a, b):
+                # a, b: per-cell positions inside the tet
+                outp = np.zeros((len(cells), 3), np.float32)
+                outk = np.zeros(len(cells), np.int64)
+                for qa in range(4):
+                    for qb in range(4):
+                        m = (a == qa) & (b == qb)
+                        if m.any():
+                            p, k = edge_vertex(cells[m], q[qa], q[qb])
+                            outp[m], outk[m] = p, k
+                return outp, outk
+            tris = []
+            if ni == 1:
+                tris.append((ev(pin[:, 0], pout[:, 0]), ev(pin[:, 0], pout[:, 1]), ev(pin[:, 0], pout[:, 2])))
+            elif ni == 3:
+                tris.append((ev(pout[:, 0], pin[:, 0]), ev(pout[:, 0], pin[:, 1]), ev(pout[:, 0], pin[:, 2])))
+            else:
+                p00, p01 = ev(pin[:, 0], pout[:, 0]), ev(pin[:, 0], pout[:, 1])
+                p11, p10 = ev(pin[:, 1], pout[:, 1]), ev(pin[:, 1], pout[:, 0])
+                tris.append((p00, p01, p11))
+                tris.append((p00, p11, p10))
+            for sub, (A, B, Cc) in enumerate(tris):
+                Bp = np.where(flip[:, None], Cc[0], B[0]); Cp = np.where(flip[:, None], B[0], Cc[0])
+                Bk = np.where(flip, Cc[1], B[1]); Ck = np.where(flip, B[1], Cc[1])
+                verts_out.append(np.stack([A[0], Bp, Cp], 1))
+                keys_out.append(np.stack([A[1], Bk, Ck], 1))
+                order.append(np.stack([cells, np.full(len(cells), t), np.full(len(cells), sub)], 1))
+    if not verts_out:
+        return np.zeros((0, 3, 3), np.float32), np.zeros((0, 3), np.int64)
+    V, K, O = np.concatenate(verts_out), np.concatenate(keys_out), np.concatenate(order)
+    perm = np.lexsort((O[:, 2], O[:, 1], O[:, 0]))
+    return V[perm], K[perm]
+
+
+def weld_triangles(verts, keys):
+    """(verts [T,3,3], keys [T,3]) -> (vertices [V,3], faces [F,3]) like bundlesdf_b200.ops.marching_tets."""
+    uniq, first, inv = np.unique(keys.reshape(-1), return_index=True, return_inverse=True)
+    vertices = verts.reshape(-1, 3)[first]
+    faces = inv.reshape(-1, 3)
+    keep = (faces[:, 0] != faces[:, 1]) & (faces[:, 1] != faces[:, 2]) & (faces[:, 0] != faces[:, 2])
+    return vertices, faces[keep]

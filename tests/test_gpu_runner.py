@@ -77,6 +77,15 @@ def test_training_reduces_loss_and_recovers_geometry(amp):
     assert sdf.item() < 0.0
     assert r.adam_step_count.item() == 120
     assert r.amp_scaler.found_inf.item() == 0
+    # extract_mesh (nerf_runner.py:1351-1409) on the trained field: a closed surface inside the bounding box, roughly jug-sized
+    mesh, sigma, pts = r.extract_mesh(voxel_size=0.01, isolevel=0.0, return_sigma=True)
+    assert mesh is not None and len(mesh.faces) > 200
+    v = np.asarray(mesh.vertices)
+    assert np.abs(v).max() <= 1.0
+    from bundlesdf_b200.mesh import TriMesh
+    assert TriMesh(v, np.asarray(mesh.faces)).is_watertight
+    extent = (v.max(0) - v.min(0)) / r.cfg['sc_factor']                  # metres: the synthetic jug is 0.10 x 0.10 x ~0.23
+    assert 0.05 < extent.min() and extent.max() < 0.45, extent
 
 
 def test_train_api_and_checkpoint_roundtrip(tmp_path):
