@@ -75,7 +75,7 @@ __global__ void adam_finish_kernel(int32_t* step_ptr, float* scale_state, int32_
 #define NOF_ADAM_MINB 4
 #endif
 __global__ void __launch_bounds__(ADAM_THREADS, NOF_ADAM_MINB) adam_kernel(const AdamArgs a, int32_t* step_ptr, float* scale_state, int32_t* found_inf,
-                                                            unsigned long long* tick) {
+                                                            unsigned long long* tick, int do_finish) {
   const uint32_t tile = blockIdx.x;
   int si = 0;
 #pragma unroll
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(ADAM_THREADS, NOF_ADAM_MINB) adam_kernel(const
     }
   }
   // ---- the last CTA to get here does the scalar bookkeeping (every CTA has read step/scale/found_inf by then): saves a launch
-  if (step_ptr) {
+  if (step_ptr && do_finish) {
     __syncthreads();                                        // every thread of this CTA has consumed the scalars (its stores depend on them)
     if (threadIdx.x == 0) {                                 // no fence: the bookkeeping touches nothing the other CTAs write
       if (atomicAdd(step_ptr + 4, 1) == (int)gridDim.x - 1) {
@@ -175,9 +175,9 @@ __global__ void __launch_bounds__(ADAM_THREADS, NOF_ADAM_MINB) adam_kernel(const
 
 using namespace nof;
 
-extern "C" int nof_adam_step(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, float eps, int32_t* step,
-                             float* scale_state, int32_t* found_inf, uint64_t* tick, nof_stream_t stream) {
-  NOF_REQUIRE(segs && n_segs >= 1 && n_segs <= ADAM_MAX_SEGS, "nof_adam_step: n_segs=%d (1..%d)", n_segs, ADAM_MAX_SEGS);
+static int adam_launch(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, float eps, int32_t* step, float* scale_state,
+                       int32_t* found_inf, uint64_t* tick, bool finish, const char* fn, nof_stream_t stream) {
+  NOF_REQUIRE(segs && n_segs >= 1 && n_segs <= ADAM_MAX_SEGS, "%s: n_segs=%d (1..%d)", fn, n_segs, ADAM_MAX_SEGS);
   AdamArgs a;
   a.n_segs = n_segs;
   a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
@@ -186,25 +186,43 @@ extern "C" int nof_adam_step(const NofAdamSeg* segs, int n_segs, float beta1, fl
     a.tile_begin[i] = (uint32_t)tiles;
     if (i < n_segs) {
       a.seg[i] = segs[i];
-      NOF_REQUIRE(segs[i].param && segs[i].grad && segs[i].exp_avg && segs[i].exp_avg_sq, "nof_adam_step: null pointer in segment %d", i);
+      NOF_REQUIRE(segs[i].param && segs[i].grad && segs[i].exp_avg && segs[i].exp_avg_sq, "%s: null pointer in segment %d", fn, i);
       NOF_REQUIRE(((uintptr_t)segs[i].param | (uintptr_t)segs[i].grad | (uintptr_t)segs[i].exp_avg | (uintptr_t)segs[i].exp_avg_sq) % 16 == 0,
-                  "nof_adam_step: segment %d not 16-byte aligned", i);
-      NOF_REQUIRE(!segs[i].shadow_f16 || (uintptr_t)segs[i].shadow_f16 % 8 == 0, "nof_adam_step: shadow of segment %d not 8-byte aligned", i);
+                  "%s: segment %d not 16-byte aligned", fn, i);
+      NOF_REQUIRE(!segs[i].shadow_f16 || (uintptr_t)segs[i].shadow_f16 % 8 == 0, "%s: shadow of segment %d not 8-byte aligned", fn, i);
       tiles += div_up<uint64_t>(segs[i].n, ADAM_TILE);
     } else {
       a.seg[i] = NofAdamSeg{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0.f, nullptr};
     }
   }
   a.tile_begin[ADAM_MAX_SEGS] = (uint32_t)tiles;
-  NOF_REQUIRE(tiles < 0x7fffffffull, "nof_adam_step: too many elements");
+  NOF_REQUIRE(tiles < 0x7fffffffull, "%s: too many elements", fn);
   cudaStream_t st = as_stream(stream);
   unsigned long long* tk = reinterpret_cast<unsigned long long*>(tick);
   if (tiles > 0) {
-    adam_kernel<<<(uint32_t)tiles, ADAM_THREADS, 0, st>>>(a, step, scale_state, found_inf, tk);
+    adam_kernel<<<(uint32_t)tiles, ADAM_THREADS, 0, st>>>(a, step, scale_state, found_inf, tk, finish ? 1 : 0);
     int rc = check_launch("adam_kernel");
     if (rc) return rc;
-    if (step) return NOF_OK;                                 // the kernel's last CTA did the bookkeeping
+    if (step || !finish) return NOF_OK;                      // bookkeeping done by the kernel's last CTA / not asked for
   }
+  if (!finish) return NOF_OK;
   adam_finish_kernel<<<1, 1, 0, st>>>(step, scale_state, found_inf, tk, beta1, beta2);
+  return check_launch("adam_finish_kernel");
+}
+
+extern "C" int nof_adam_step(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, float eps, int32_t* step,
+                             float* scale_state, int32_t* found_inf, uint64_t* tick, nof_stream_t stream) {
+  return adam_launch(segs, n_segs, beta1, beta2, eps, step, scale_state, found_inf, tick, true, "nof_adam_step", stream);
+}
+
+extern "C" int nof_adam_update(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, float eps, const int32_t* step,
+                               const float* scale_state, const int32_t* found_inf, nof_stream_t stream) {
+  return adam_launch(segs, n_segs, beta1, beta2, eps, const_cast<int32_t*>(step), const_cast<float*>(scale_state),
+                     const_cast<int32_t*>(found_inf), nullptr, false, "nof_adam_update", stream);
+}
+
+extern "C" int nof_adam_finish(int32_t* step, float* scale_state, int32_t* found_inf, uint64_t* tick, float beta1, float beta2,
+                               nof_stream_t stream) {
+  adam_finish_kernel<<<1, 1, 0, as_stream(stream)>>>(step, scale_state, found_inf, reinterpret_cast<unsigned long long*>(tick), beta1, beta2);
   return check_launch("adam_finish_kernel");
 }

@@ -209,6 +209,14 @@ class NerfRunner:
         # learning rates (one per param group) and the RNG tick the sampler adds to its Philox offset
         self.lr_dev = torch.tensor([g['lr'] for g in groups], dtype=torch.float32, device=dev)
         self.tick = torch.zeros(1, dtype=torch.int64, device=dev)
+        # cfg 'defer_table_update': the hash table's Adam pass (the big HBM stream of the optimizer) of step k runs at the START of
+        # step k+1 on a side stream, concurrently with that step's pose correction + ray march (which only need the pose segment's
+        # update); everything that reads the table from outside goes through synchronize_parameters() first.
+        self._defer = bool(self.cfg.get('defer_table_update', False))
+        self._table_pending = False
+        self._table_stream = torch.cuda.Stream(priority=0) if self._defer else None
+        self.march_tick = torch.zeros(1, dtype=torch.int64, device=dev)     # sampler RNG tick of the deferred mode (bumped after every march)
+        self.lr_table_dev = self.lr_dev[:1].clone()                         # learning rate of the pending table update (lags lr_dev by one step)
         self._graph = None
         self._eager_steps = 0
         segs = [dict(name='table', param=self.table.view(-1), grad=z(self.table).view(-1), exp_avg=z(self.table).view(-1),
@@ -352,6 +360,7 @@ class NerfRunner:
 
     def add_new_frames(self, images, depths, masks, normal_maps, poses, occ_masks=None, new_pcd=None, reuse_weights=False):
         """nerf_runner.py:352-433."""
+        self.synchronize_parameters()
         prev_n = len(self.images)
         down = int(self.cfg['down_scale_ratio'])
         images, depths, masks = images[:, ::down, ::down], depths[:, ::down, ::down], masks[:, ::down, ::down]
@@ -418,7 +427,7 @@ class NerfRunner:
         self._step_buf = b
         return b
 
-    def _forward_backward(self, batch, t_rand=None, taps=None):
+    def _forward_backward(self, batch, t_rand=None, taps=None, tick=None, before_fused=None):
         """Launches pose correction, ray march and the fused forward+loss+backward for `batch` [N,12]. Gradients accumulate into
         the flat grad buffers (scaled by the loss scale); nothing synchronises."""
         cfg = self.cfg
@@ -431,11 +440,15 @@ class NerfRunner:
         ops.pose_forward(pa.data.data if pa is not None else None, self.c2w_array, cfg['max_trans'] * sc, cfg['max_rot'], out=b['tf'])
         ops.ray_march(batch, b['tf'], self.octree_m.occ_bits, self.octree_m.level, cfg['N_samples'], cfg['N_samples_around_depth'], trunc,
                       cfg['near'] * sc, cfg['far'] * sc, cfg['neg_trunc_ratio'], t_rand=t_rand, perturb=bool(cfg.get('perturb', 1)),
-                      seed=0x5DEECE66D, offset=0, offset_ptr=self.tick, z_vals=b['z_vals'], err_flag=b['march_err'])
+                      seed=0x5DEECE66D, offset=0, offset_ptr=(tick if tick is not None else self.tick), z_vals=b['z_vals'], err_flag=b['march_err'])
+        if tick is not None:
+            tick.add_(1)
         ops.fill_step_cfg(sb, cfg, trunc)
         sb.set(rays=batch)
         for k in ('rgb_map', 'raw', 'valid_samples', 'weights'):
             sb.set(**{k: (taps.get(k) if taps else None)})
+        if before_fused is not None:
+            before_fused()
         sb.launch()                                         # zeroes b['losses'] and b['grad_tf'] itself
         if pa is not None:
             ops.pose_backward(pa.data.data, self.c2w_array, b['grad_tf'], self.adam_segs['pose']['grad'].view(-1, 6), cfg['max_trans'] * sc,
@@ -450,11 +463,56 @@ class NerfRunner:
             self.adam_segs['pose']['grad'].view(-1, 6)[1:].add_(d / d.norm().clamp(min=1e-12) * cfg['pose_reg_weight'])
         return b
 
+    def _adam_scalars(self):
+        return (self._adam_step_buf, self.amp_scaler.state if self.amp_scaler.enabled else None, self.amp_scaler.found_inf)
+
     def _optimizer_step(self):
         groups = self.optimizer.param_groups
         segs = [dict(s, lr=groups[s['group']]['lr']) for s in self.adam_segs.values()]
-        ops.adam_step(segs, 0.9, 0.999, 1e-15, self._adam_step_buf, self.amp_scaler.state if self.amp_scaler.enabled else None,
-                      self.amp_scaler.found_inf, tick=self.tick)
+        step, scale, inf = self._adam_scalars()
+        ops.adam_step(segs, 0.9, 0.999, 1e-15, step, scale, inf, tick=self.tick)
+
+    def _table_update(self):
+        """The deferred half of an optimizer step: Adam on the table segment, then the step's bookkeeping."""
+        step, scale, inf = self._adam_scalars()
+        seg = dict(self.adam_segs['table'], lr=self.optimizer.param_groups[0]['lr'], lr_ptr=self.lr_table_dev.data_ptr())
+        ops.adam_update([seg], 0.9, 0.999, 1e-15, step, scale, inf)
+        ops.adam_finish(0.9, 0.999, step, scale, inf, tick=self.tick)
+        self.lr_table_dev.copy_(self.lr_dev[:1])            # the update issued at the end of the CURRENT step uses the current rate
+
+    def synchronize_parameters(self):
+        """Apply a pending (deferred) table update. Called by every method that exposes the table; call it yourself before reading
+        `models['embed_fn'].embeddings` or the optimizer state directly when cfg['defer_table_update'] is on."""
+        if self._table_pending:
+            self._table_update()
+            self._table_pending = False
+
+    def _step(self, batch, t_rand=None):
+        """Forward, backward and optimizer of one step on the current stream (also what the CUDA graph captures)."""
+        if not self._defer:
+            b = self._forward_backward(batch, t_rand=t_rand)
+            self._optimizer_step()
+            return b
+        main = torch.cuda.current_stream()
+        pending, side = self._table_pending, self._table_stream
+        if pending:                                         # fork: table update of the PREVIOUS step
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._table_update()
+
+        def join():                                         # the fused kernel is the first reader of the table
+            if pending:
+                main.wait_stream(side)
+            else:
+                self.lr_table_dev.copy_(self.lr_dev[:1])
+
+        b = self._forward_backward(batch, t_rand=t_rand, tick=self.march_tick, before_fused=join)
+        groups = self.optimizer.param_groups
+        small = [dict(s, lr=groups[s['group']]['lr']) for k, s in self.adam_segs.items() if k != 'table']
+        step, scale, inf = self._adam_scalars()
+        ops.adam_update(small, 0.9, 0.999, 1e-15, step, scale, inf)
+        self._table_pending = True
+        return b
 
     def _graph_usable(self, t_rand):
         return (t_rand is None and bool(self.cfg.get('use_cuda_graph', True)) and self.cfg.get('trunc_decay_type', '') == '')
@@ -463,39 +521,45 @@ class NerfRunner:
         """Replay (capturing it on first use) a CUDA graph of the whole step: pose correction, ray march, fused
         forward/loss/backward, pose backward, Adam. Every launch argument is static: the batch lives in a fixed buffer, the
         learning rates, loss scale, Adam step and RNG tick live in device memory."""
-        g = self._graph
-        if g is None or g['N'] != batch.shape[0]:
+        key = (batch.shape[0], self._table_pending)
+        if not isinstance(self._graph, dict) or 'N' in self._graph:
+            self._graph = {}
+        g = self._graph.get(key)
+        if g is None:
             if self._eager_steps < 2:                       # first steps run eagerly (buffer allocation, kernel attributes)
                 self._eager_steps += 1
-                self._forward_backward(batch)
-                self._optimizer_step()
-                return self._step_buf
-            static = torch.empty_like(batch)
+                return self._step(batch)
+            statics = [x['batch'] for x in self._graph.values() if x['batch'].shape == batch.shape]
+            static = statics[0] if statics else torch.empty_like(batch)
             static.copy_(batch)
-            side = torch.cuda.Stream()
+            # capture stream = high priority: in the deferred mode its latency-bound kernels (pose correction, ray march) run next to
+            # the table's Adam pass (normal-priority side stream) and must get SM slots as that kernel's CTAs retire
+            side = torch.cuda.Stream(priority=-1 if self._defer else 0)
             side.wait_stream(torch.cuda.current_stream())
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
-                self._forward_backward(static)
-                self._optimizer_step()
-            self._graph = g = dict(N=batch.shape[0], graph=graph, batch=static, buf=self._step_buf)
+                self._step(static)
+            self._graph[key] = g = dict(graph=graph, batch=static, buf=self._step_buf)
         elif batch.data_ptr() != g['batch'].data_ptr():
             g['batch'].copy_(batch)
         g['graph'].replay()
+        if self._defer:
+            self._table_pending = True
         self._step_buf = g['buf']                           # the buffers the graph writes (a render() may have swapped them)
         return g['buf']
 
     def step_batch_buffer(self):
         """The static batch buffer of the captured step (gather straight into it to skip one copy), or None."""
-        return self._graph['batch'] if self._graph is not None else None
+        if not self._graph:
+            return None
+        return next(iter(self._graph.values()))['batch']
 
     def train_loop(self, batch, t_rand=None):
         """One train step (reference nerf_runner.py:679-852): forward, losses, backward, optimizer step, lr schedule."""
         if self._graph_usable(t_rand):
             b = self._step_graphed(batch)
         else:
-            b = self._forward_backward(batch, t_rand=t_rand)
-            self._optimizer_step()
+            b = self._step(batch, t_rand=t_rand)
         if self.global_step % 10 == 0 and self.global_step > 0:
             self.schedule_lr()
         cfg = self.cfg
@@ -534,6 +598,7 @@ class NerfRunner:
                 batch = next(self.data_loader)
             self.train_loop(batch)
             self.global_step += 1
+        self.synchronize_parameters()
 
     # ------------------------------------------------------------------ evaluation helpers (downstream of the path)
     @torch.no_grad()
@@ -541,6 +606,7 @@ class NerfRunner:
                near=None, far=None):
         """Reference nerf_runner.py:1172-1198 contract: returns [rgb_map, extras] with extras['raw','z_vals','valid_samples',
         'weights']. Evaluated by the fused kernel with taps; the gradients it also produces are discarded."""
+        self.synchronize_parameters()
         N = rays.shape[0]
         S = self.cfg['N_samples'] + self.cfg['N_samples_around_depth']
         dev = self.device
@@ -565,6 +631,7 @@ class NerfRunner:
     @torch.no_grad()
     def run_network_density(self, inputs, get_normals=False):
         """nerf_runner.py:1307-1347 (SDF only): inputs [..,3] in normalised space -> sdf [..,1]."""
+        self.synchronize_parameters()
         if get_normals:
             raise NotImplementedError('normals from run_network_density are not built')
         flat = inputs.reshape(-1, 3).float().contiguous().to(self.device)
@@ -577,6 +644,7 @@ class NerfRunner:
         GPU: the SDF sweep on the native query kernel, the surface on nof_marching_tets (the reference calls
         skimage's Lewiner marching cubes on the host: same surface up to the triangulation inside a cell, not the same triangles).
         Returns a `trimesh.Trimesh` when trimesh is installed (like the reference), else `bundlesdf_b200.mesh.TriMesh`."""
+        self.synchronize_parameters()
         vs = voxel_size * self.cfg['sc_factor']
         bounds = np.array(self.cfg['bounding_box']).reshape(2, 3)
         axes = [np.arange(bounds[0, i] + 0.5 * vs, bounds[1, i], vs) for i in range(3)]
@@ -609,6 +677,7 @@ class NerfRunner:
 
     # ------------------------------------------------------------------ checkpoints (nerf_runner.py:528-576)
     def save_weights(self, out_file, models):
+        self.synchronize_parameters()
         data = {'global_step': self.global_step, 'model': models['model'].state_dict(), 'optimizer': self.optimizer.state_dict(),
                 'embed_fn': models['embed_fn'].state_dict()}
         if models.get('embeddirs_fn') is not None:
@@ -628,6 +697,7 @@ class NerfRunner:
             shutil.copyfile(out_file, latest)
 
     def load_weights(self, ckpt_path):
+        self._table_pending = False                         # whatever was pending is overwritten by the checkpoint
         ckpt = torch.load(ckpt_path, map_location=self.device, weights_only=False)
         self.models['model'].load_state_dict(ckpt['model'])            # copies INTO the flat-buffer views
         self.models['embed_fn'].load_state_dict(ckpt['embed_fn'])

@@ -118,19 +118,44 @@ def fill_step_cfg(sb, cfg, trunc):
     sb.set_scalars(**{k: float(cfg.get(k, 0)) for k in LOSS_CFG_KEYS})
 
 
-def adam_step(segs, beta1, beta2, eps, step, scale_state=None, found_inf=None, tick=None):
-    """segs: list of dict(param, grad, exp_avg, exp_avg_sq, shadow_f16|None, lr). step: device int32 tensor [8] (include/nof.h:
-    [0] update count, the rest library scratch) or None."""
-    if step is not None and (step.numel() < 8 or step.dtype != torch.int32):
-        raise _lib.NofError('nof_adam_step: `step` must be a device int32[8] tensor (see include/nof.h)')
-    lib = _lib.load()
+def _adam_segs(segs):
     arr = (NofAdamSeg * len(segs))()
     for i, s in enumerate(segs):
         n = s['param'].numel()
         arr[i] = NofAdamSeg(_lib.ptr(s['param']), _lib.ptr(s['grad']), _lib.ptr(s['exp_avg']), _lib.ptr(s['exp_avg_sq']),
                             _lib.ptr(s.get('shadow_f16')), n, float(s['lr']), s.get('lr_ptr'))
+    return arr
+
+
+def _check_step_buf(step):
+    if step is not None and (step.numel() < 8 or step.dtype != torch.int32):
+        raise _lib.NofError('nof_adam_*: `step` must be a device int32[8] tensor (see include/nof.h)')
+
+
+def adam_step(segs, beta1, beta2, eps, step, scale_state=None, found_inf=None, tick=None):
+    """segs: list of dict(param, grad, exp_avg, exp_avg_sq, shadow_f16|None, lr). step: device int32 tensor [8] (include/nof.h:
+    [0] update count, the rest library scratch) or None."""
+    _check_step_buf(step)
+    lib = _lib.load()
+    arr = _adam_segs(segs)
     _lib.check(lib.nof_adam_step(arr, len(segs), float(beta1), float(beta2), float(eps), _lib.ptr(step), _lib.ptr(scale_state),
                                  _lib.ptr(found_inf), _lib.ptr(tick), _lib.stream()), 'nof_adam_step')
+
+
+def adam_update(segs, beta1, beta2, eps, step, scale_state=None, found_inf=None):
+    """nof_adam_update: the update of `segs` only (reads step / scale / found_inf, modifies none of them)."""
+    _check_step_buf(step)
+    lib = _lib.load()
+    arr = _adam_segs(segs)
+    _lib.check(lib.nof_adam_update(arr, len(segs), float(beta1), float(beta2), float(eps), _lib.ptr(step), _lib.ptr(scale_state),
+                                   _lib.ptr(found_inf), _lib.stream()), 'nof_adam_update')
+
+
+def adam_finish(beta1, beta2, step, scale_state=None, found_inf=None, tick=None):
+    """nof_adam_finish: the bookkeeping of one optimizer step after all nof_adam_update launches of that step."""
+    _check_step_buf(step)
+    _lib.check(_lib.load().nof_adam_finish(_lib.ptr(step), _lib.ptr(scale_state), _lib.ptr(found_inf), _lib.ptr(tick), float(beta1),
+                                           float(beta2), _lib.stream()), 'nof_adam_finish')
 
 
 def query_sdf(sb, x, out=None):

@@ -213,6 +213,15 @@ typedef struct {
  *   tick: optional device uint64 incremented on EVERY call (feeds NofMarchCfg.offset_ptr). */
 int nof_adam_step(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, float eps, int32_t* step,
                   float* scale_state, int32_t* found_inf, uint64_t* tick, nof_stream_t stream);
+/* The same pass split in two, for callers that update groups of segments in separate launches (e.g. the big table on a side
+ * stream, overlapped with the next step's ray marching — NerfRunner cfg 'defer_table_update'): nof_adam_update applies the update
+ * to `segs` reading step / scale_state / found_inf without modifying them; nof_adam_finish does the bookkeeping of
+ * nof_adam_step (step count, cached bias corrections, GradScaler growth/backoff, found_inf reset, tick) once all updates of the
+ * step have been issued. nof_adam_step == nof_adam_update on all segments + nof_adam_finish, in one launch. */
+int nof_adam_update(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, float eps, const int32_t* step,
+                    const float* scale_state, const int32_t* found_inf, nof_stream_t stream);
+int nof_adam_finish(int32_t* step, float* scale_state, int32_t* found_inf, uint64_t* tick, float beta1, float beta2,
+                    nof_stream_t stream);
 
 /* SDF-only inference for mesh extraction (run_network_density, nerf_runner.py:1307-1347 with
  * NeRFSmall.forward_sdf nerf_helpers.py:296-302): x [P,3] in [-1,1] (clipped inside) -> sdf [P]. */

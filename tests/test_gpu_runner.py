@@ -142,11 +142,12 @@ def test_render_contract():
     assert float(r.adam_segs['table']['grad'].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize('amp', [False, True])
-def test_training_trajectory_matches_oracle(amp):
+@pytest.mark.parametrize('amp,defer', [(False, False), (True, False), (True, True)])
+def test_training_trajectory_matches_oracle(amp, defer):
     """same init, same batches, same jitter -> the loss trajectory and the optimised parameters of the CUDA path
-    follow the CPU oracle (torch autograd + the oracle's Adam) over 25 optimizer steps."""
-    r, seq = _runner(amp, n_frames=4, N=192)
+    follow the CPU oracle (torch autograd + the oracle's Adam) over 25 optimizer steps. `defer`: the table's Adam pass of step k
+    runs at the start of step k+1 on a side stream (cfg defer_table_update) — same trajectory."""
+    r, seq = _runner(amp, n_frames=4, N=192, defer_table_update=defer)
     steps = 25
     enc = r.models['embed_fn']
     P = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in r.models['model'].state_dict().items()}
@@ -187,3 +188,35 @@ def test_training_trajectory_matches_oracle(amp):
     rel = lambda a, w: np.linalg.norm(a - w) / max(np.linalg.norm(w), 1e-30)
     assert rel(r.models['model'].state_dict()['color_net.4.weight'].cpu().numpy(), P['color_net.4.weight'].detach().numpy()) < (0.1 if amp else 0.03)
     assert rel(r.models['pose_array'].data.detach().cpu().numpy(), P['pose_data'].detach().numpy()) < (0.2 if amp else 0.1)
+    r.synchronize_parameters()
+    assert r.adam_step_count.item() == steps
+    tab = rel(enc.embeddings.detach().cpu().numpy(), P['embeddings'].detach().numpy())
+    assert tab < (0.35 if amp else 0.15), tab
+
+
+def test_deferred_table_update_graph_path_matches_plain():
+    """cfg defer_table_update with CUDA-graph replay (two graph variants: with / without a pending update) against the plain step
+    order: same batches -> same losses within the noise of the atomics, same Adam step count after synchronize_parameters()."""
+    ra, _ = _runner(True, n_frames=4, N=256)
+    rb, _ = _runner(True, n_frames=4, N=256, defer_table_update=True)
+    la, lb = [], []
+    for it in range(40):
+        batch = next(ra.data_loader)
+        next(rb.data_loader)
+        ra.train_loop(batch)
+        rb.train_loop(batch.clone())
+        ra.global_step += 1
+        rb.global_step += 1
+        if it == 17:                                        # an external reader in the middle: flushes, next step has nothing pending
+            sa, _ = ra.run_network_density(torch.zeros(1, 3, device='cuda'))
+            sb_, _ = rb.run_network_density(torch.zeros(1, 3, device='cuda'))
+            assert abs(sa.item() - sb_.item()) < 5e-2 * max(abs(sa.item()), 0.05)
+        if it % 5 == 4:
+            la.append(ra.get_metrics()['loss'])
+            lb.append(rb.get_metrics()['loss'])
+    rb.synchronize_parameters()
+    assert rb.adam_step_count.item() == ra.adam_step_count.item() == 40
+    assert rb.tick.item() == ra.tick.item() == 40 and rb.march_tick.item() == 40
+    np.testing.assert_allclose(lb, la, rtol=0.05)
+    rel = lambda a, w: float((a - w).norm() / w.norm())
+    assert rel(rb.table, ra.table) < 0.2 and rel(rb.mlp_flat, ra.mlp_flat) < 0.1
