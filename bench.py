@@ -318,8 +318,14 @@ def main():
     t_setup = time.perf_counter() - t_setup
     N = c['N']
 
-    def step_resident():
-        batch = next(runner.data_loader)
+    from bundlesdf_b200 import ops as nof_ops
+
+    def step_resident():                                # the body of NerfRunner.train(): gather straight into the captured step's input
+        buf = runner.step_batch_buffer()
+        if buf is not None:
+            batch = nof_ops.gather_rays(runner.rays, runner.data_loader.next_ids().contiguous(), out=buf)
+        else:
+            batch = next(runner.data_loader)
         runner.train_loop(batch)
         runner.global_step += 1
 
