@@ -217,7 +217,7 @@ class NerfRunner:
         self._table_stream = torch.cuda.Stream(priority=0) if self._defer else None
         self.march_tick = torch.zeros(1, dtype=torch.int64, device=dev)     # sampler RNG tick of the deferred mode (bumped after every march)
         self.lr_table_dev = self.lr_dev[:1].clone()                         # learning rate of the pending table update (lags lr_dev by one step)
-        self._graph = None
+        self._graph = {}                                    # captured step graphs by (batch size, table update pending)
         self._eager_steps = 0
         segs = [dict(name='table', param=self.table.view(-1), grad=z(self.table).view(-1), exp_avg=z(self.table).view(-1),
                      exp_avg_sq=z(self.table).view(-1), shadow_f16=(self.table_f16.view(-1) if self.table_f16 is not None else None), group=0),
@@ -395,7 +395,7 @@ class NerfRunner:
             self.rays = torch.cat((self.rays, rays), dim=0).contiguous()     # stays on the device (the reference moves it to the CPU, :431)
         self.data_loader = DataLoader(rays=self.rays, batch_size=self.cfg['N_rand'])
         self._step_buf = None
-        self._graph = None
+        self._graph = {}                                    # captured step graphs by (batch size, table update pending)
 
     # ------------------------------------------------------------------ the hot path
     def _ensure_step_buffers(self, N):
@@ -522,8 +522,6 @@ class NerfRunner:
         forward/loss/backward, pose backward, Adam. Every launch argument is static: the batch lives in a fixed buffer, the
         learning rates, loss scale, Adam step and RNG tick live in device memory."""
         key = (batch.shape[0], self._table_pending)
-        if not isinstance(self._graph, dict) or 'N' in self._graph:
-            self._graph = {}
         g = self._graph.get(key)
         if g is None:
             if self._eager_steps < 2:                       # first steps run eagerly (buffer allocation, kernel attributes)
@@ -731,4 +729,4 @@ class NerfRunner:
         del live
         self.global_step = int(ckpt.get('global_step', 0))
         self._step_buf = None
-        self._graph = None
+        self._graph = {}                                    # captured step graphs by (batch size, table update pending)
