@@ -371,6 +371,86 @@ def ray_trace_intervals(occ, rays_o, rays_d, i_max=None):
     return res
 
 
+def ray_trace_intervals_merge(occ, rays_o, rays_d, i_max=None):
+    """Same result as ray_trace_intervals, bit for bit, WITHOUT the sequential walk: the design check for a warp-parallel
+    ray_march kernel. The exit time of a cell through the k-th plane of axis a, T_a[k] = (plane(ix0_a + k step_a) -
+    o_a) * inv_a, is a closed form of k (the walk never accumulates t), non-decreasing in k (every operation is a monotone rounding),
+    so the walk is the merge of three sorted lists ordered by (T, axis) — `ta < t_out` with axes tried in order 0,1,2 is exactly that
+    tie rule. Step m leaves through event m; its cell is the start cell advanced by the per-axis event counts before m; t_in(m) =
+    min(T[m-1], t1) (t0 for m = 0); the walk ends at the first event that leaves the grid (the last crossing of its axis) or reaches
+    t1. All of it is data-parallel over events; only the packing rule (a stop flag and a running count) needs a prefix scan."""
+    f32 = np.float32
+    n = occ.shape[0]
+    cell = f32(2.0) / f32(n)
+    N = len(rays_o)
+    out = []
+    for r in range(N):
+        o = rays_o[r].astype(f32)
+        d = rays_d[r].astype(f32)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            inv = f32(1.0) / d
+        t0, t1 = f32(0.0), f32(np.inf)
+        hit = True
+        for a in range(3):
+            if d[a] == 0:
+                if o[a] < -1 or o[a] > 1:
+                    hit = False
+                continue
+            ta = (f32(-1.0) - o[a]) * inv[a]
+            tb = (f32(1.0) - o[a]) * inv[a]
+            lo, hi = (ta, tb) if ta <= tb else (tb, ta)
+            t0 = max(t0, lo)
+            t1 = min(t1, hi)
+        packed = []
+        if hit and t0 < t1:
+            ix0 = np.zeros(3, np.int64)
+            step = np.zeros(3, np.int64)
+            for a in range(3):
+                p = o[a] + t0 * d[a]
+                c = int(np.floor((p + f32(1.0)) / cell))
+                ix0[a] = min(max(c, 0), n - 1)
+                step[a] = 1 if d[a] > 0 else (-1 if d[a] < 0 else 0)
+            Ts, axs, ks, last = [], [], [], []
+            for a in range(3):
+                if step[a] == 0:
+                    continue
+                K = int(n - ix0[a]) if step[a] > 0 else int(ix0[a] + 1)          # crossings until the walk leaves the grid on this axis
+                k = np.arange(K, dtype=np.int64)
+                ixa = ix0[a] + k * step[a]
+                plane = (ixa + (1 if step[a] > 0 else 0)).astype(f32) * cell - f32(1.0)
+                T = ((plane - o[a]).astype(f32) * inv[a]).astype(f32)
+                Ts.append(T); axs.append(np.full(K, a)); ks.append(k); last.append(k == K - 1)
+            if Ts:
+                T = np.concatenate(Ts); ax = np.concatenate(axs); kk = np.concatenate(ks); is_last = np.concatenate(last)
+                order = np.lexsort((kk, ax, T))                                  # by T, ties: lower axis first, then k
+                T, ax, is_last = T[order], ax[order], is_last[order]
+                M = len(T)
+                t_out = np.minimum(T, t1)
+                t_in = np.concatenate([[t0], t_out[:-1]]).astype(f32)
+                cnt = np.zeros((M, 3), np.int64)                                 # events of each axis before step m
+                for a in range(3):
+                    cnt[:, a] = np.concatenate([[0], np.cumsum(ax == a)[:-1]])
+                cells = ix0[None, :] + cnt * step[None, :]
+                stop = is_last | (t_out >= t1)
+                m_end = int(np.argmax(stop)) if stop.any() else M - 1
+                m_end = min(m_end, 3 * n + 2)                                    # the walk's guard (never binding: M <= 3n)
+                sel = np.arange(M) <= m_end
+                o_m = occ[cells[:, 0].clip(0, n - 1), cells[:, 1].clip(0, n - 1), cells[:, 2].clip(0, n - 1)] & sel
+                # packing rule (common.cu:137-148) over the occupied steps, in order
+                zero = o_m & ((t_in == 0) | (t_out == 0))
+                first_zero = int(np.argmax(zero)) if zero.any() else M
+                keep = o_m & (np.arange(M) < first_zero) & ~(t_in > t_out) & ~(np.abs((t_out - t_in).astype(f32)).astype(np.float64) < 1e-4)
+                packed = [(a_, b_) for a_, b_ in zip(t_in[keep], t_out[keep])]
+        out.append(packed)
+    I = max(1, max(len(p) for p in out)) if i_max is None else i_max
+    res = np.zeros((N, I, 2), dtype=f32)
+    for r, p in enumerate(out):
+        for k, (a, b) in enumerate(p[:I]):
+            res[r, k, 0] = a
+            res[r, k, 1] = b
+    return res
+
+
 def postprocess_octree_ray_tracing(ray_index, depth_in_out, unique_ids, start_poss, max_intersections, n_rays):
     """common.cu:129-167 verbatim semantics on CPU (numpy)."""
     out = np.zeros((n_rays, max_intersections, 2), np.float32)

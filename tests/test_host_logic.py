@@ -132,3 +132,27 @@ def test_nerf_runner_refuses_to_run_without_cuda():
     from bundlesdf_b200.nerf_runner import NerfRunner
     with pytest.raises(NofError):
         NerfRunner(syn.default_cfg(), None, None, None, None, None, np.eye(3), build_octree_pcd=syn.PointCloud(np.zeros((1, 3))))
+
+
+def test_ray_walk_as_merge_of_axis_crossings_is_bit_identical():
+    """Design check for a warp-parallel ray march: the voxel walk restated as the merge of three closed-form
+    per-axis crossing lists gives exactly the sequential walk's intervals, including axis-aligned rays, rays with zero components,
+    origins inside the grid and origins on cell planes."""
+    rng = np.random.default_rng(0)
+    for n in (8, 16, 32):
+        occ = rng.random((n, n, n)) < 0.3
+        N = 300
+        o = (rng.random((N, 3)) * 3 - 1.5).astype(np.float32)
+        tgt = (rng.random((N, 3)) * 1.6 - 0.8).astype(np.float32)
+        d = tgt - o
+        d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        d[:30] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 30)] * rng.choice([-1, 1], (30, 1)).astype(np.float32)
+        d[30:60, rng.integers(0, 3)] = 0
+        nn = np.linalg.norm(d[30:60], axis=1, keepdims=True)
+        d[30:60] = (d[30:60] / np.where(nn == 0, 1, nn)).astype(np.float32)
+        o[60:150] = (rng.random((90, 3)) * 1.8 - 0.9).astype(np.float32)
+        o[150:180] = np.round(o[150:180] * n / 2) / (n / 2)
+        a = O.ray_trace_intervals(occ, o, d)
+        b = O.ray_trace_intervals_merge(occ, o, d, i_max=a.shape[1])
+        np.testing.assert_array_equal(a, b)
+        assert (a[:, 0, 0] != 0).sum() > N // 2
