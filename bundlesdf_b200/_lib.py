@@ -21,6 +21,12 @@ class NofMarchCfg(C.Structure):
                 ('seed', _u64), ('offset', _u64), ('offset_ptr', _vp)]
 
 
+class NofPrologue(C.Structure):
+    _fields_ = [('pool', _vp), ('ids', _vp), ('n_ids', _i64), ('batch', _vp), ('N', _i32), ('ray_dim', _i32), ('cursor', _vp),
+                ('pose_data', _vp), ('c2w', _vp), ('tf', _vp), ('F', _i32), ('max_trans', _f32), ('max_rot_deg', _f32),
+                ('tick', _vp), ('done', _vp)]
+
+
 class NofStep(C.Structure):
     _fields_ = [('N', _i32), ('S', _i32), ('L', _i32), ('C', _i32), ('F', _i32), ('ff', _i32), ('ray_dim', _i32), ('amp', _i32),
                 ('S_log2', _f32), ('H', _i32), ('offsets', _vp), ('table_f32', _vp), ('table_f16', _vp),
@@ -48,6 +54,7 @@ _SIGS = {
     'nof_postprocess_octree_ray_tracing': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     'nof_gather_rays': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     'nof_pose_forward': (C.c_int, [_vp, _vp, _vp, C.c_int, _f32, _f32, _vp]),
+    'nof_step_prologue': (C.c_int, [C.POINTER(NofPrologue), _vp]),
     'nof_pose_backward': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _f32, _f32, _vp, _vp]),
     'nof_ray_march': (C.c_int, [C.POINTER(NofMarchCfg), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'nof_mlp_param_count': (_sz, [C.c_int, C.c_int]),

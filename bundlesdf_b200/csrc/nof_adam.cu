@@ -43,6 +43,10 @@ __device__ __forceinline__ void adam_finish(int32_t* step_ptr, float* scale_stat
   if (tick) *tick += 1ull;
   const bool inf = found_inf && (*found_inf != 0);
   if (!inf && step_ptr) *step_ptr += 1;
+  if (inf && step_ptr) {
+    step_ptr[5] += 1;                                       // skipped updates so far (GradScaler back-offs)
+    if (*found_inf == 2) step_ptr[7] = 1;                   // sticky: the step kernel reported INVALID results (tcgen05 wait timed out)
+  }
   if (step_ptr) {                                           // cache the NEXT update's bias corrections (torch computes them in fp64)
     const int next = *step_ptr + 1;
     float bc[2];

@@ -3,6 +3,8 @@
 // followed by tf = dT @ c2w (nerf_runner.py:1051-1053). One thread per frame; the backward evaluates the same
 // expression tree on forward-mode dual numbers (6 tangents = the 6 pose parameters) and contracts with grad_tf, so it
 // is the exact derivative of the forward code — replacing ~60 tiny autograd kernels per step with two launches.
+#include <algorithm>
+
 #include "nof_common.cuh"
 
 namespace nof {
@@ -124,10 +126,8 @@ __device__ __forceinline__ void delta_pose(const typename O::T data[6], float ma
   }
 }
 
-__global__ void pose_forward_kernel(const float* __restrict__ pose_data, const float* __restrict__ c2w, float* __restrict__ tf,
-                                    int F, float max_trans, float max_rot_deg) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
+__device__ __forceinline__ void pose_forward_frame(const float* __restrict__ pose_data, const float* __restrict__ c2w, float* __restrict__ tf,
+                                                   int f, float max_trans, float max_rot_deg) {
   const float* A = c2w + (size_t)f * 16;
   float M[12];
   if (pose_data == nullptr || f == 0) {        // frame 0 is pinned to identity (nerf_helpers.py:151-153)
@@ -146,6 +146,42 @@ __global__ void pose_forward_kernel(const float* __restrict__ pose_data, const f
       float acc = M[i * 4 + 0] * A[0 * 4 + j] + M[i * 4 + 1] * A[1 * 4 + j] + M[i * 4 + 2] * A[2 * 4 + j] + M[i * 4 + 3] * A[3 * 4 + j];
       tf[(size_t)f * 12 + i * 4 + j] = acc;
     }
+}
+
+__global__ void pose_forward_kernel(const float* __restrict__ pose_data, const float* __restrict__ c2w, float* __restrict__ tf,
+                                    int F, float max_trans, float max_rot_deg) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < F) pose_forward_frame(pose_data, c2w, tf, f, max_trans, max_rot_deg);
+}
+
+// Everything a train step does before the ray march, in ONE launch (each of the pieces is launch-latency-sized): the batch gather
+// from the device-resident ray pool at a DEVICE-resident cursor (so that a CUDA graph can hold many consecutive steps), the pose
+// correction of all frames, and the bump of the sampler's RNG tick and of the cursor. The counters are advanced by the last CTA to
+// finish (completion ticket), i.e. after every CTA has read them.
+__global__ void __launch_bounds__(256) step_prologue_kernel(const NofPrologue p) {
+  __shared__ long long s_base;
+  if (threadIdx.x == 0) s_base = (p.pool && p.cursor) ? *p.cursor : 0;
+  __syncthreads();
+  const long long base = s_base;
+  const int gid = blockIdx.x * 256 + threadIdx.x, gsz = gridDim.x * 256;
+  if (p.pool) {
+    const int total = p.N * p.ray_dim;
+    for (int i = gid; i < total; i += gsz) {
+      const int r = i / p.ray_dim, c = i - r * p.ray_dim;
+      long long k = base + r;
+      if (k >= p.n_ids) k -= p.n_ids;                       // never taken when the host keeps whole batches inside an epoch
+      p.batch[i] = __ldg(p.pool + (size_t)p.ids[k] * p.ray_dim + c);
+    }
+  }
+  for (int f = gid; f < p.F; f += gsz) pose_forward_frame(p.pose_data, p.c2w, p.tf, f, p.max_trans, p.max_rot_deg);
+  if (p.done) {
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(p.done, 1) == (int)gridDim.x - 1) {
+      *p.done = 0;
+      if (p.pool && p.cursor) *p.cursor = base + p.N;
+      if (p.tick) *p.tick += 1ull;
+    }
+  }
 }
 
 __global__ void pose_backward_kernel(const float* __restrict__ pose_data, const float* __restrict__ c2w,
@@ -195,6 +231,15 @@ extern "C" int nof_pose_forward(const float* pose_data, const float* c2w, float*
   if (F == 0) return NOF_OK;
   pose_forward_kernel<<<div_up(F, 64), 64, 0, as_stream(stream)>>>(pose_data, c2w, tf, F, max_trans, max_rot_deg);
   return check_launch("pose_forward_kernel");
+}
+
+extern "C" int nof_step_prologue(const NofPrologue* p, nof_stream_t stream) {
+  NOF_REQUIRE(p && p->c2w && p->tf && p->F >= 1, "nof_step_prologue: null pose pointers or F < 1");
+  NOF_REQUIRE(!p->pool || (p->ids && p->batch && p->N >= 1 && p->ray_dim >= 1 && p->n_ids >= p->N), "nof_step_prologue: bad gather arguments");
+  NOF_REQUIRE(p->done || !(p->cursor || p->tick), "nof_step_prologue: counters need the `done` ticket");
+  const int work = std::max(p->pool ? p->N * p->ray_dim : 0, p->F);
+  step_prologue_kernel<<<std::max(1, std::min(div_up(work, 256), 128)), 256, 0, as_stream(stream)>>>(*p);
+  return check_launch("step_prologue_kernel");
 }
 
 extern "C" int nof_pose_backward(const float* pose_data, const float* c2w, const float* grad_tf, float* grad_pose, int F,

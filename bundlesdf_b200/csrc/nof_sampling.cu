@@ -355,11 +355,8 @@ extern "C" int nof_ray_march(const NofMarchCfg* cfg, const float* rays, const fl
   if (cfg->N == 0) return NOF_OK;
   const int n = 1 << cfg->level;
   const size_t smem = (size_t)((n * n * n + 31) / 32) * 4 + (size_t)MARCH_WARPS * cfg->I_max * 4 * sizeof(float) + 2 * MARCH_WARPS * sizeof(int);
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  if (smem > 48 * 1024)      // per-device attribute: set whenever it is needed, not once per process
     cudaFuncSetAttribute(ray_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
-  }
   NOF_REQUIRE(smem <= 100 * 1024, "nof_ray_march: shared memory %zu too large", smem);
   int sms = 148;
   nof_device_info(&sms, nullptr);

@@ -687,11 +687,8 @@ size_t step_amp_smem(int PT, int KE) { return (size_t)make_plan(PT, KE).total; }
 template <int PT, int KE>
 static int launch_amp(const StepArgs& a, int blocks, cudaStream_t st) {
   const size_t smem = step_amp_smem(PT, KE);
-  static bool once = false;
-  if (!once) {
-    cudaFuncSetAttribute(step_amp_kernel<PT, KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    once = true;
-  }
+  // function attributes are per device: set on every launch (a cheap host-side call) rather than once per process
+  cudaFuncSetAttribute(step_amp_kernel<PT, KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   step_amp_kernel<PT, KE><<<blocks, 2 * PT, smem, st>>>(a);
   return check_launch("step_amp_kernel");
 }

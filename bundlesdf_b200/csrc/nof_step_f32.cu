@@ -466,11 +466,7 @@ size_t step_f32_smem(int E, int V, int grp_pts) { return (size_t)make_f32_plan(E
 template <int E>
 static int launch_f32(const StepArgs& a, int blocks, cudaStream_t st) {
   const size_t smem = step_f32_smem(E, a.V, a.R * a.Sp);
-  static size_t set_to = 0;
-  if (smem > set_to) {
-    cudaFuncSetAttribute(step_f32_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    set_to = smem;
-  }
+  cudaFuncSetAttribute(step_f32_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per-device attribute
   step_f32_kernel<E><<<blocks, FT, smem, st>>>(a);
   return check_launch("step_f32_kernel");
 }

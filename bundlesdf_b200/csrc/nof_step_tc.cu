@@ -847,11 +847,8 @@ size_t step_tc_smem(int KE) { return (size_t)tc::make_plan(KE).total; }
 template <int KE>
 static int launch_tc(const StepArgs& a, int blocks, cudaStream_t st) {
   const size_t smem = step_tc_smem(KE);
-  static bool once = false;
-  if (!once) {
-    cudaFuncSetAttribute(tc::step_tc_kernel<KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    once = true;
-  }
+  // function attributes are per device: set on every launch (a cheap host-side call) rather than once per process
+  cudaFuncSetAttribute(tc::step_tc_kernel<KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   static_assert((size_t)(64 * KE * 2 + 16 * 64 * 2 + 64 * KC * 2 + 64 * 64 * 2 + 16 * 64 * 2 + 216 * 4 + 6 * 128 + 16) <= kWPackBytes, "wpack too small");
   tc::pack_mlp_kernel<KE><<<(tc::make_plan(KE).x0 / 4 + 255) / 256, 256, 0, st>>>(a);
   tc::step_tc_kernel<KE><<<blocks, tc::NT, smem, st>>>(a);

@@ -18,6 +18,64 @@ class TriMesh:
         self.vertices = self.vertices @ T[:3, :3].T + T[:3, 3]
         return self
 
+    def merge_vertices(self):
+        """trimesh.Trimesh.merge_vertices (bundlesdf.py:748): weld vertices with identical positions, re-index the faces, drop
+        the faces that become degenerate. extract_mesh() already welds by grid-edge key, so this is normally a no-op."""
+        uniq, inv = np.unique(self.vertices, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        if len(uniq) == len(self.vertices):
+            return self
+        if self.vertex_colors is not None:
+            first = np.full(len(uniq), -1, dtype=np.int64)
+            first[inv[::-1]] = np.arange(len(inv))[::-1]
+            self.vertex_colors = self.vertex_colors[first]
+        f = inv[self.faces]
+        self.vertices = uniq
+        self.faces = f[(f[:, 0] != f[:, 1]) & (f[:, 1] != f[:, 2]) & (f[:, 0] != f[:, 2])]
+        return self
+
+    @property
+    def edges(self):
+        """[3F,2] directed edges, trimesh order (what Utils.trimesh_split feeds to connected_components, Utils.py:290)."""
+        f = self.faces
+        return np.stack([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], 1).reshape(-1, 2)
+
+    def update_vertices(self, mask):
+        """trimesh.Trimesh.update_vertices(mask) (Utils.py:296): keep the masked vertices and the faces that only use them."""
+        mask = np.asarray(mask, dtype=bool)
+        remap = np.cumsum(mask) - 1
+        keep = mask[self.faces].all(axis=1)
+        self.faces = remap[self.faces[keep]]
+        self.vertices = self.vertices[mask]
+        if self.vertex_colors is not None:
+            self.vertex_colors = self.vertex_colors[mask]
+        return self
+
+    def split(self, min_edge=0):
+        """Connected components as separate meshes (role of Utils.trimesh_split, Utils.py:287-298: components with fewer than
+        `min_edge` vertices are dropped) — union-find over the edges, no trimesh/networkx needed."""
+        n = len(self.vertices)
+        parent = np.arange(n)
+        e = self.edges
+        for _ in range(64):                                  # pointer-jumping label propagation; converges in O(log diameter)
+            lo = np.minimum(parent[e[:, 0]], parent[e[:, 1]])
+            new = parent.copy()
+            np.minimum.at(new, e[:, 0], lo)
+            np.minimum.at(new, e[:, 1], lo)
+            new = new[new]
+            if np.array_equal(new, parent):
+                break
+            parent = new
+        out = []
+        used = np.zeros(n, dtype=bool)
+        used[self.faces.reshape(-1)] = True
+        for lab in np.unique(parent[used]):
+            mask = (parent == lab) & used
+            if mask.sum() < max(min_edge, 1):
+                continue
+            out.append(self.copy().update_vertices(mask))
+        return out
+
     @property
     def area(self):
         a, b, c = (self.vertices[self.faces[:, i]] for i in range(3))

@@ -24,8 +24,13 @@ def sampleRaysUniformOccupiedVoxels(z_in_out, z_sampled, z_vals):
         raise RuntimeError('only float32 is built (the reference dispatches float/double)')
     N, S = z_sampled.shape
     I = z_in_out.shape[1]
+    err = torch.zeros(1, dtype=torch.int32, device=z_vals.device)
     _lib.check(lib.nof_sample_rays_uniform_occupied_voxels(z_in_out.data_ptr(), z_sampled.data_ptr(), z_vals.data_ptr(),
-                                                           N, I, S, None, _lib.stream()), 'sampleRaysUniformOccupiedVoxels')
+                                                           N, I, S, err.data_ptr(), _lib.stream()), 'sampleRaysUniformOccupiedVoxels')
+    if int(err.item()) != 0:            # one host sync, like the reference's implicit one on its legacy-stream launch + later .item()s
+        raise RuntimeError('sampleRaysUniformOccupiedVoxels: a cumulative sample ran past the last interval of its ray '
+                           '(the reference kernel prints "z_remain is invalid" and never returns, common.cu:66-71,87-92); '
+                           'the affected samples were clamped to the end of the last interval')
     return z_vals
 
 

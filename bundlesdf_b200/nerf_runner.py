@@ -37,17 +37,22 @@ def set_seed(random_seed):
 
 class DataLoader:
     """Reference nerf_runner.py:90-107: epoch permutation from the CPU RNG, last partial batch dropped, reshuffle when
-    exhausted. The permutation is uploaded once per epoch; a step reads a slice of it on the device (no per-step H2D)."""
+    exhausted. The permutation is uploaded once per epoch into a FIXED device buffer; a step reads a slice of it on the device
+    (no per-step H2D), either through a host-side slice (`next_ids`, `__next__`) or at a device-resident cursor
+    (nof_step_prologue: what lets one CUDA graph hold many consecutive steps)."""
 
     def __init__(self, rays, batch_size):
         self.rays = rays
         self.batch_size = batch_size
         self.pos = 0
+        self.ids_dev = torch.empty(len(rays), dtype=torch.int64, device=rays.device)
+        self.cursor_dev = torch.zeros(1, dtype=torch.int64, device=rays.device)
+        self._dev_pos = 0                                   # what cursor_dev holds (None: unknown)
         self._shuffle()
 
     def _shuffle(self):
         self.ids = torch.randperm(len(self.rays))
-        self.ids_dev = self.ids.to(self.rays.device)
+        self.ids_dev.copy_(self.ids)
 
     def next_ids(self):
         if self.pos + self.batch_size < len(self.ids):
@@ -63,6 +68,29 @@ class DataLoader:
     def __next__(self):
         ids = self.next_ids()
         return ops.gather_rays(self.rays, ids.contiguous())
+
+    # ---- device-cursor protocol (NerfRunner.train_steps)
+    def batches_left(self):
+        """Whole batches the current epoch still holds under the reference's rule `pos + batch_size < len(ids)`."""
+        return max(0, (len(self.ids) - self.pos - 1) // self.batch_size)
+
+    def reserve(self, k):
+        """Make sure the next batches can be read at the device cursor; returns how many of the requested k are available
+        before the next reshuffle (>= 1). Reshuffling here is the reference's else-branch: new permutation, first slice [0, B)."""
+        if self.batches_left() < 1:
+            self._shuffle()
+            self.pos = 0
+        if self._dev_pos != self.pos:
+            self.cursor_dev.fill_(self.pos)
+            self._dev_pos = self.pos
+        return min(k, self.batches_left())
+
+    def consumed(self, k):
+        """Host bookkeeping after k steps gathered at the device cursor."""
+        last = self.pos + (k - 1) * self.batch_size
+        self.batch_ray_ids = self.ids[last:last + self.batch_size]
+        self.pos += k * self.batch_size
+        self._dev_pos = self.pos
 
 
 class GradScalerState:
@@ -215,7 +243,8 @@ class NerfRunner:
         self._defer = bool(self.cfg.get('defer_table_update', False))
         self._table_pending = False
         self._table_stream = torch.cuda.Stream(priority=0) if self._defer else None
-        self.march_tick = torch.zeros(1, dtype=torch.int64, device=dev)     # sampler RNG tick of the deferred mode (bumped after every march)
+        self.march_tick = torch.zeros(1, dtype=torch.int64, device=dev)     # sampler RNG tick, bumped by every step prologue
+        self._done_ticket = torch.zeros(1, dtype=torch.int32, device=dev)   # CTA completion ticket of nof_step_prologue
         self.lr_table_dev = self.lr_dev[:1].clone()                         # learning rate of the pending table update (lags lr_dev by one step)
         self._graph = {}                                    # captured step graphs by (batch size, table update pending)
         self._eager_steps = 0
@@ -427,9 +456,10 @@ class NerfRunner:
         self._step_buf = b
         return b
 
-    def _forward_backward(self, batch, t_rand=None, taps=None, tick=None, before_fused=None):
-        """Launches pose correction, ray march and the fused forward+loss+backward for `batch` [N,12]. Gradients accumulate into
-        the flat grad buffers (scaled by the loss scale); nothing synchronises."""
+    def _forward_backward(self, batch, t_rand=None, taps=None, before_fused=None, gather=False):
+        """Launches the step prologue (pose correction of all frames; with `gather` also the batch gather from the ray pool at the
+        data loader's device cursor, into `batch`), the ray march and the fused forward+loss+backward for `batch` [N,12].
+        Gradients accumulate into the flat grad buffers (scaled by the loss scale); nothing synchronises."""
         cfg = self.cfg
         sc = cfg['sc_factor']
         batch = batch.contiguous()
@@ -437,12 +467,13 @@ class NerfRunner:
         sb = b['sb']
         pa = self.models['pose_array']
         trunc = self.get_truncation()
-        ops.pose_forward(pa.data.data if pa is not None else None, self.c2w_array, cfg['max_trans'] * sc, cfg['max_rot'], out=b['tf'])
+        dl = self.data_loader
+        ops.step_prologue(pa.data.data if pa is not None else None, self.c2w_array, b['tf'], cfg['max_trans'] * sc, cfg['max_rot'],
+                          pool=(self.rays if gather else None), ids=(dl.ids_dev if gather else None), batch=batch,
+                          cursor=(dl.cursor_dev if gather else None), tick=self.march_tick, done=self._done_ticket)
         ops.ray_march(batch, b['tf'], self.octree_m.occ_bits, self.octree_m.level, cfg['N_samples'], cfg['N_samples_around_depth'], trunc,
                       cfg['near'] * sc, cfg['far'] * sc, cfg['neg_trunc_ratio'], t_rand=t_rand, perturb=bool(cfg.get('perturb', 1)),
-                      seed=0x5DEECE66D, offset=0, offset_ptr=(tick if tick is not None else self.tick), z_vals=b['z_vals'], err_flag=b['march_err'])
-        if tick is not None:
-            tick.add_(1)
+                      seed=0x5DEECE66D, offset=0, offset_ptr=self.march_tick, z_vals=b['z_vals'], err_flag=b['march_err'])
         ops.fill_step_cfg(sb, cfg, trunc)
         sb.set(rays=batch)
         for k in ('rgb_map', 'raw', 'valid_samples', 'weights'):
@@ -451,8 +482,10 @@ class NerfRunner:
             before_fused()
         sb.launch()                                         # zeroes b['losses'] and b['grad_tf'] itself
         if pa is not None:
+            # the pose gradient stays multiplied by the loss scale like every other segment: nof_adam_step unscales ONCE
+            # (GradScaler.unscale_, nerf_runner.py:756-760)
             ops.pose_backward(pa.data.data, self.c2w_array, b['grad_tf'], self.adam_segs['pose']['grad'].view(-1, 6), cfg['max_trans'] * sc,
-                              cfg['max_rot'], self.amp_scaler.state if self.amp_scaler.enabled else None)
+                              cfg['max_rot'], None)
         # host-side tiny terms (nerf_runner.py:743-752): feature regulariser, pose regulariser
         fa = self.models['feature_array']
         scale = self.amp_scaler.state[0] if self.amp_scaler.enabled else 1.0
@@ -460,7 +493,7 @@ class NerfRunner:
             self.adam_segs['feat']['grad'].add_(fa.data.data.view(-1) * (2.0 * cfg['feature_reg_weight'] / fa.data.numel() * scale))
         if pa is not None and cfg.get('pose_reg_weight', 0) > 0:
             d = pa.data.data[1:]
-            self.adam_segs['pose']['grad'].view(-1, 6)[1:].add_(d / d.norm().clamp(min=1e-12) * cfg['pose_reg_weight'])
+            self.adam_segs['pose']['grad'].view(-1, 6)[1:].add_(d / d.norm().clamp(min=1e-12) * (cfg['pose_reg_weight'] * scale))
         return b
 
     def _adam_scalars(self):
@@ -487,10 +520,10 @@ class NerfRunner:
             self._table_update()
             self._table_pending = False
 
-    def _step(self, batch, t_rand=None):
-        """Forward, backward and optimizer of one step on the current stream (also what the CUDA graph captures)."""
+    def _step(self, batch, t_rand=None, gather=False):
+        """Forward, backward and optimizer of one step on the current stream (also what the CUDA graphs capture)."""
         if not self._defer:
-            b = self._forward_backward(batch, t_rand=t_rand)
+            b = self._forward_backward(batch, t_rand=t_rand, gather=gather)
             self._optimizer_step()
             return b
         main = torch.cuda.current_stream()
@@ -506,7 +539,7 @@ class NerfRunner:
             else:
                 self.lr_table_dev.copy_(self.lr_dev[:1])
 
-        b = self._forward_backward(batch, t_rand=t_rand, tick=self.march_tick, before_fused=join)
+        b = self._forward_backward(batch, t_rand=t_rand, before_fused=join, gather=gather)
         groups = self.optimizer.param_groups
         small = [dict(s, lr=groups[s['group']]['lr']) for k, s in self.adam_segs.items() if k != 'table']
         step, scale, inf = self._adam_scalars()
@@ -517,27 +550,39 @@ class NerfRunner:
     def _graph_usable(self, t_rand):
         return (t_rand is None and bool(self.cfg.get('use_cuda_graph', True)) and self.cfg.get('trunc_decay_type', '') == '')
 
+    def _static_batch(self, N):
+        if getattr(self, '_batch_static', None) is None or self._batch_static.shape[0] != N:
+            self._batch_static = torch.empty(N, 12, device=self.device)
+        return self._batch_static
+
+    def _capture(self, key, n_steps, gather):
+        """Capture `n_steps` consecutive steps reading the static batch buffer (gather=False: the caller fills it; gather=True:
+        every step's prologue gathers its batch into it at the data loader's device cursor). Every launch argument is static:
+        learning rates, loss scale, Adam step, RNG tick and the batch cursor live in device memory."""
+        static = self._batch_static
+        # capture stream = high priority: in the deferred mode its latency-bound kernels (prologue, ray march) run next to
+        # the table's Adam pass (normal-priority side stream) and must get SM slots as that kernel's CTAs retire
+        side = torch.cuda.Stream(priority=-1 if self._defer else 0)
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(n_steps):
+                self._step(static, gather=gather)
+        self._graph[key] = g = dict(graph=graph, batch=static, buf=self._step_buf)
+        return g
+
     def _step_graphed(self, batch):
-        """Replay (capturing it on first use) a CUDA graph of the whole step: pose correction, ray march, fused
-        forward/loss/backward, pose backward, Adam. Every launch argument is static: the batch lives in a fixed buffer, the
-        learning rates, loss scale, Adam step and RNG tick live in device memory."""
-        key = (batch.shape[0], self._table_pending)
+        """Replay (capturing it on first use) a CUDA graph of one whole step on an explicit batch: prologue, ray march, fused
+        forward/loss/backward, pose backward, Adam."""
+        N = batch.shape[0]
+        key = ('one', N, self._table_pending)
         g = self._graph.get(key)
         if g is None:
             if self._eager_steps < 2:                       # first steps run eagerly (buffer allocation, kernel attributes)
                 self._eager_steps += 1
                 return self._step(batch)
-            statics = [x['batch'] for x in self._graph.values() if x['batch'].shape == batch.shape]
-            static = statics[0] if statics else torch.empty_like(batch)
-            static.copy_(batch)
-            # capture stream = high priority: in the deferred mode its latency-bound kernels (pose correction, ray march) run next to
-            # the table's Adam pass (normal-priority side stream) and must get SM slots as that kernel's CTAs retire
-            side = torch.cuda.Stream(priority=-1 if self._defer else 0)
-            side.wait_stream(torch.cuda.current_stream())
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                self._step(static)
-            self._graph[key] = g = dict(graph=graph, batch=static, buf=self._step_buf)
+            self._static_batch(N).copy_(batch)
+            g = self._capture(key, 1, gather=False)
         elif batch.data_ptr() != g['batch'].data_ptr():
             g['batch'].copy_(batch)
         g['graph'].replay()
@@ -552,12 +597,13 @@ class NerfRunner:
             return None
         return next(iter(self._graph.values()))['batch']
 
-    def train_loop(self, batch, t_rand=None):
-        """One train step (reference nerf_runner.py:679-852): forward, losses, backward, optimizer step, lr schedule."""
-        if self._graph_usable(t_rand):
-            b = self._step_graphed(batch)
-        else:
-            b = self._step(batch, t_rand=t_rand)
+    def _host_action_after(self, g):
+        """Does the host do something after step index g (lr schedule, checkpoint, metrics print; nerf_runner.py:762-815)?"""
+        cfg = self.cfg
+        return (g % 10 == 0 and g > 0) or (g % cfg['i_weights'] == 0 and g > 0) or (g % cfg['i_print'] == 0)
+
+    def _after_step(self):
+        """Host side of train_loop after the launches of step `self.global_step` (nerf_runner.py:762-815)."""
         if self.global_step % 10 == 0 and self.global_step > 0:
             self.schedule_lr()
         cfg = self.cfg
@@ -565,10 +611,73 @@ class NerfRunner:
             self.save_weights(out_file=os.path.join(cfg['save_dir'], 'model_latest.pth'), models=self.models)
         if self.global_step % cfg['i_print'] == 0:
             logging.info(f'Iter: {self.global_step}, ' + ', '.join(f'{k}: {v:.7f}' for k, v in self.get_metrics().items()))
+
+    def train_steps(self, n):
+        """`n` consecutive train steps (what train() loops over: draw a batch from the ray pool, train_loop, global_step += 1),
+        with the host out of the loop: batches are gathered ON THE DEVICE at the data loader's cursor, and runs of
+        cfg['graph_block_steps'] (default 10) steps that need no host action in between (lr schedule every 10 steps, checkpoints,
+        metric prints) replay as ONE CUDA graph. Same trajectory as calling train_loop(next(data_loader)) n times."""
+        K = max(1, int(self.cfg.get('graph_block_steps', 10)))
+        N = self.cfg['N_rand']
+        dl = self.data_loader
+        done = 0
+        while done < n:
+            if not self._graph_usable(None) or self._eager_steps < 2:
+                self._eager_steps += 1
+                dl.reserve(1)
+                self._step(self._static_batch(N), gather=True)
+                k = 1
+            else:
+                k = min(K, n - done)
+                for j in range(k - 1):                      # a block ends at the first step the host has to act after
+                    if self._host_action_after(self.global_step + j):
+                        k = j + 1
+                        break
+                k = dl.reserve(k)
+                if k < K:
+                    k = 1
+                key = ('blk', N, k, self._table_pending)
+                g = self._graph.get(key)
+                if g is None:
+                    self._static_batch(N)
+                    g = self._capture(key, k, gather=True)  # capturing does not execute: replay below runs these k steps
+                g['graph'].replay()
+                if self._defer:
+                    self._table_pending = True
+                self._step_buf = g['buf']
+            dl.consumed(k)
+            self.global_step += k - 1                       # the host acts once, after the block's last step
+            self._after_step()
+            self.global_step += 1
+            done += k
+
+    def train_loop(self, batch, t_rand=None):
+        """One train step (reference nerf_runner.py:679-852): forward, losses, backward, optimizer step, lr schedule."""
+        if self._graph_usable(t_rand):
+            b = self._step_graphed(batch)
+        else:
+            b = self._step(batch, t_rand=t_rand)
+        self._after_step()
         return b
+
+    def check_device_flags(self):
+        """Device-side error flags, read at the points that synchronise anyway (get_metrics, end of train()): the sampler's
+        interval-list overflow / walk mismatch (the reference prints and spins, common.cu:66-71) and the fused kernel's
+        'results invalid' report. Raises NofError; the flags are cleared so that a caller may continue."""
+        msgs = []
+        b = self._step_buf
+        if b is not None and int(b['march_err'].item()) != 0:
+            b['march_err'].zero_()
+            msgs.append('ray march: interval list overflow or sample walk past the last interval (samples were clamped)')
+        if int(self._adam_step_buf[7].item()) != 0:
+            self._adam_step_buf[7] = 0
+            msgs.append('fused step kernel reported invalid results (tensor-core wait timed out); those steps were skipped')
+        if msgs:
+            raise _lib.NofError('; '.join(msgs))
 
     def get_metrics(self):
         """Loss terms of the LAST step with the reference's metric names (nerf_runner.py:794-815). Synchronises."""
+        self.check_device_flags()
         l = self._step_buf['losses'].cpu().numpy()
         m = {'loss': float(l[0]), 'rgb_loss': float(l[1]), 'rgb0_loss': 0.0, 'fs_rgb_loss': float(l[4]), 'depth_loss': 0.0, 'depth_loss0': 0.0,
              'fs_loss': float(l[2]), 'point_cloud_loss': 0.0, 'point_cloud_normal_loss': 0.0, 'sdf_loss': float(l[3]), 'eikonal_loss': 0.0,
@@ -584,19 +693,12 @@ class NerfRunner:
         return m
 
     def train(self):
-        """nerf_runner.py:855-863."""
+        """nerf_runner.py:855-863: N_iters = n_step + 1 steps from the ray pool."""
         set_seed(0)
-        for it in range(self.N_iters):
-            if it % max(self.N_iters // 10, 1) == 0:
-                logging.info(f'train progress {it}/{self.N_iters}')
-            buf = self.step_batch_buffer()
-            if buf is not None:                               # gather straight into the captured step's input buffer
-                batch = ops.gather_rays(self.rays, self.data_loader.next_ids().contiguous(), out=buf)
-            else:
-                batch = next(self.data_loader)
-            self.train_loop(batch)
-            self.global_step += 1
+        logging.info(f'train: {self.N_iters} steps')
+        self.train_steps(self.N_iters)
         self.synchronize_parameters()
+        self.check_device_flags()
 
     # ------------------------------------------------------------------ evaluation helpers (downstream of the path)
     @torch.no_grad()
@@ -673,8 +775,18 @@ class NerfRunner:
             return mesh, sigma, grid
         return mesh
 
+    def mesh_texture_from_train_images(self, mesh, discard_ids=[], tex_res=1024):
+        """nerf_runner.py:1468-1543 (called by bundlesdf.py:763 when run_custom.py asks for a textured mesh). Offline texture baking
+        on top of common.rayColorToTextureImageCUDA is outside the hot path this package rebuilds (SURVEY.md §2 #4c, §8 'out of
+        scope'): raise a clear error instead of an AttributeError; the geometry from extract_mesh() is complete without it."""
+        raise NotImplementedError('mesh_texture_from_train_images (texture baking, reference nerf_runner.py:1468) is out of scope of '
+                                  'bundlesdf_b200: call the reference implementation with this mesh, or keep the untextured mesh')
+
     # ------------------------------------------------------------------ checkpoints (nerf_runner.py:528-576)
     def save_weights(self, out_file, models):
+        """Same keys as the reference. `octree` differs in content: a dict {occ, level, max_level} (dense occupancy) instead of
+        kaolin's octree byte tensor, so the reference's loader cannot rebuild ITS OctreeManager from it (and vice versa: see
+        load_weights); every other entry is interchangeable."""
         self.synchronize_parameters()
         data = {'global_step': self.global_step, 'model': models['model'].state_dict(), 'optimizer': self.optimizer.state_dict(),
                 'embed_fn': models['embed_fn'].state_dict()}
@@ -704,7 +816,13 @@ class NerfRunner:
         if self.models['pose_array'] is not None:
             self.models['pose_array'].load_state_dict(ckpt['pose_array'])
         if 'octree' in ckpt:
-            self.octree_m = OctreeManager(octree=ckpt['octree'], device=self.device)
+            if isinstance(ckpt['octree'], dict):
+                self.octree_m = OctreeManager(octree=ckpt['octree'], device=self.device)
+            else:
+                # a checkpoint written by the reference stores kaolin's octree byte tensor (nerf_runner.py:565-566), which only
+                # kaolin can decode: keep the occupancy built from build_octree_pcd (same cloud -> same cells, nerf_runner.py:436-489)
+                logging.warning('load_weights: checkpoint carries a kaolin octree blob; occupancy rebuilt from build_octree_pcd instead')
+                self.build_octree()
         if self.table_f16 is not None:
             self.table_f16.copy_(self.table)
         # optimizer moments: copy into the aliased flat buffers (keeps the kernels' pointers valid)

@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import NofAdamSeg, NofMarchCfg, NofStep
+from ._lib import NofAdamSeg, NofMarchCfg, NofPrologue, NofStep
 
 
 def mlp_param_layout(E, V):
@@ -58,6 +58,17 @@ def pose_backward(pose_data, c2w, grad_tf, grad_pose, max_trans, max_rot_deg, lo
     _lib.check(lib.nof_pose_backward(_lib.ptr(pose_data), _lib.ptr(c2w), _lib.ptr(grad_tf), _lib.ptr(grad_pose), c2w.shape[0],
                                      float(max_trans), float(max_rot_deg), _lib.ptr(loss_scale), _lib.stream()), 'nof_pose_backward')
     return grad_pose
+
+
+def step_prologue(pose_data, c2w, tf, max_trans, max_rot_deg, pool=None, ids=None, batch=None, cursor=None, tick=None, done=None):
+    """nof_step_prologue: [batch gather at the device cursor] + pose correction of all frames + counter bumps, one launch."""
+    lib = _lib.load()
+    F = c2w.shape[0]
+    p = NofPrologue(_lib.ptr(pool), _lib.ptr(ids), int(ids.shape[0]) if ids is not None else 0, _lib.ptr(batch),
+                    int(batch.shape[0]) if batch is not None else 0, int(batch.shape[1]) if batch is not None else 0, _lib.ptr(cursor),
+                    _lib.ptr(pose_data), _lib.ptr(c2w), _lib.ptr(tf), F, float(max_trans), float(max_rot_deg), _lib.ptr(tick), _lib.ptr(done))
+    _lib.check(lib.nof_step_prologue(C.byref(p), _lib.stream()), 'nof_step_prologue')
+    return tf
 
 
 def gather_rays(pool, ids, out=None):

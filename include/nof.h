@@ -107,6 +107,27 @@ int nof_pose_forward(const float* pose_data, const float* c2w, float* tf, int F,
 int nof_pose_backward(const float* pose_data, const float* c2w, const float* grad_tf, float* grad_pose, int F,
                       float max_trans, float max_rot_deg, const float* loss_scale_or_null, nof_stream_t stream);
 
+/* Everything of a train step that precedes the ray march, in one launch: DataLoader.__next__ (nerf_runner.py:97-107) at a
+ * DEVICE-resident cursor + PoseArray.get_matrices / `dT @ c2w` for all frames (see nof_gather_rays / nof_pose_forward) + the
+ * counters. With the cursor in device memory a captured CUDA graph can hold many consecutive steps (NerfRunner.train_steps). */
+typedef struct {
+  const float* pool;        /* [R,ray_dim] ray pool, or NULL: no gather (the caller filled `batch`) */
+  const int64_t* ids;       /* [n_ids] epoch permutation */
+  int64_t n_ids;
+  float* batch;             /* [N,ray_dim] out */
+  int N, ray_dim;
+  int64_t* cursor;          /* device scalar: index into `ids` of this step's first ray; advanced by N (the host keeps whole
+                               batches inside an epoch and rewrites the cursor when it reshuffles) */
+  const float* pose_data;   /* [F,6] or NULL */
+  const float* c2w;         /* [F,4,4] */
+  float* tf;                /* [F,12] out */
+  int F;
+  float max_trans, max_rot_deg;
+  uint64_t* tick;           /* optional device counter, +1 per call (NofMarchCfg.offset_ptr: the sampler's RNG stream position) */
+  int32_t* done;            /* device int32, zero-initialised: CTA completion ticket (required when cursor or tick is given) */
+} NofPrologue;
+int nof_step_prologue(const NofPrologue* p, nof_stream_t stream);
+
 typedef struct {
   int N;                /* rays in the batch */
   int ray_dim;          /* floats per ray row: 12 = dir3 rgb3 depth mask frame type near far (nerf_runner.py:259-300) */
@@ -206,7 +227,9 @@ typedef struct {
  * (nerf_runner.py:492-504, 756-761): exact dense Adam (betas, eps, no weight decay), single pass:
  * read g,m,v,p -> write p,m,v,(fp16 shadow) and zero g. Skips the update when *found_inf != 0.
  *   step: device int32[8]: [0] = number of Adam updates applied so far (incremented inside unless the step is skipped);
- *         [1..7] = scratch owned by the library (fp32 bias corrections cached for update [3], CTA completion counter [4]);
+ *         [1..7] = owned by the library (fp32 bias corrections cached for update [3], CTA completion counter [4],
+ *         [5] = number of skipped updates so far, [7] = sticky error flag: set when found_inf carried the value 2, i.e. the
+ *         step kernel reported invalid results (a bounded tensor-core wait timed out) rather than an fp16 overflow);
  *         zero-initialise all eight. NULL = no step counter (bias corrections recomputed, bookkeeping in a second launch).
  *   scale_state: device float[2] = {loss_scale, growth_tracker} updated like GradScaler (init 65536,
  *                x2 every 2000 clean steps, x0.5 on inf) or NULL when amp is off.

@@ -50,7 +50,7 @@ def test_single_step_gradients_match_oracle_through_runner(amp):
     assert rel(r.models['embed_fn'].embeddings.grad.cpu().numpy() / scale, P['embeddings'].grad.numpy()) < gtol
     for k, p in r.models['model'].named_parameters():
         assert rel(p.grad.cpu().numpy() / scale, sd[k].grad.numpy()) < gtol, k
-    assert rel(r.models['pose_array'].data.grad.cpu().numpy(), P['pose_data'].grad.numpy()) < 2 * gtol
+    assert rel(r.models['pose_array'].data.grad.cpu().numpy() / scale, P['pose_data'].grad.numpy()) < 2 * gtol   # scaled like every segment
     assert rel(r.models['feature_array'].data.grad.cpu().numpy() / scale, P['feature_data'].grad.numpy()) < gtol
     m = r.get_metrics()
     assert abs(m['loss'] - float(ref['loss'].detach())) <= (5e-3 if amp else 2e-4) * abs(float(ref['loss'].detach()))
@@ -216,7 +216,56 @@ def test_deferred_table_update_graph_path_matches_plain():
             lb.append(rb.get_metrics()['loss'])
     rb.synchronize_parameters()
     assert rb.adam_step_count.item() == ra.adam_step_count.item() == 40
-    assert rb.tick.item() == ra.tick.item() == 40 and rb.march_tick.item() == 40
+    assert rb.tick.item() == ra.tick.item() == 40 and rb.march_tick.item() == ra.march_tick.item() == 40
     np.testing.assert_allclose(lb, la, rtol=0.05)
     rel = lambda a, w: float((a - w).norm() / w.norm())
     assert rel(rb.table, ra.table) < 0.2 and rel(rb.mlp_flat, ra.mlp_flat) < 0.1
+
+
+def test_train_steps_blocks_match_per_step_loop():
+    """NerfRunner.train_steps: batches gathered on the device at the loader's cursor and runs of 10 steps replayed as ONE CUDA graph
+    (bench.py's timed region, and what train() uses) against the per-step public loop train_loop(next(data_loader)): same
+    permutation -> same batches, same sampler ticks -> the same trajectory within the noise of the atomics."""
+    ra, _ = _runner(True, n_frames=4, N=256)
+    rb, _ = _runner(True, n_frames=4, N=256)
+    n = 47                                                  # 2 eager + singles up to step 10 + 10-step blocks + a tail
+    for it in range(n):
+        ra.train_loop(next(ra.data_loader))
+        ra.global_step += 1
+    rb.train_steps(n)
+    assert rb.global_step == ra.global_step == n
+    assert rb.adam_step_count.item() == ra.adam_step_count.item() == n
+    assert rb.march_tick.item() == ra.march_tick.item() == n
+    assert rb.data_loader.pos == ra.data_loader.pos
+    assert torch.equal(rb.data_loader.batch_ray_ids, ra.data_loader.batch_ray_ids)
+    assert any(k[0] == 'blk' and k[2] == 10 for k in rb._graph), list(rb._graph)
+    assert float(rb.lr_dev[0]) == pytest.approx(float(ra.lr_dev[0]), rel=1e-6) and float(rb.lr_dev[0]) < 0.01
+    la, lb = ra.get_metrics(), rb.get_metrics()
+    for k in ('loss', 'rgb_loss', 'sdf_loss', 'fs_loss'):
+        assert lb[k] == pytest.approx(la[k], rel=0.05), k
+    rel = lambda a, w: float((a - w).norm() / w.norm())
+    assert rel(rb.table, ra.table) < 0.2 and rel(rb.mlp_flat, ra.mlp_flat) < 0.1
+
+
+def test_pose_regulariser_follows_the_loss_scale():
+    """pose_reg_weight > 0 under AMP: the regulariser's gradient is added to the (loss-scaled) pose gradient buffer multiplied by the
+    loss scale, so that the single unscale inside nof_adam_step recovers d/dpose [pose_reg_weight * ||data[1:]||] (nerf_runner.py:748-758)."""
+    r, _ = _runner(True, n_frames=4, N=128, pose_reg_weight=0.5)
+    with torch.no_grad():
+        r.models['pose_array'].data.normal_(0, 0.1)
+    batch = next(r.data_loader)
+    t_rand = torch.rand(batch.shape[0], 128, device='cuda')
+    r.cfg['pose_reg_weight'] = 0.0
+    r._forward_backward(batch, t_rand=t_rand)
+    g0 = r.adam_segs['pose']['grad'].clone().view(-1, 6)
+    for s_ in r.adam_segs.values():
+        s_['grad'].zero_()
+    r.cfg['pose_reg_weight'] = 0.5
+    r._forward_backward(batch, t_rand=t_rand)
+    g1 = r.adam_segs['pose']['grad'].clone().view(-1, 6)
+    d = r.models['pose_array'].data.detach()[1:]
+    want = 0.5 * d / d.norm()
+    scale = r.amp_scaler.get_scale()
+    got = (g1 - g0)[1:] / scale
+    assert torch.allclose(got, want, rtol=2e-2, atol=2e-3 * float(want.abs().max())), (got, want)
+    assert float((g1 - g0)[0].abs().max()) == 0.0

@@ -1,0 +1,81 @@
+"""GPU parity of the fused step AT THE BENCHMARKED SIZES (BASELINE.json configs[1] "C2" and configs[2] "C3"): one fused
+forward+loss+backward of 2048 / 4096 rays x 128 samples, 16 levels, T = 2^19, pose refinement on, against the CPU oracle
+(reference nerf_runner.py:679-758 restated in oracle/nof_oracle.py) with exact autograd gradients.
+
+The small cases of test_gpu_step.py give every persistent CTA at most one tile; here every CTA walks several tiles, so the
+tile ticket loop, the weight-gradient accumulators that persist across tiles, the mbarrier phase carry-over and the per-tile
+ray re-setup are all exercised (the test asserts n_groups > resident CTAs). Same tolerances as test_gpu_step.py:
+  fp32 policy: forward <= 1e-4 rel, losses <= 2e-4 rel, gradients <= 2e-3 of max |g|
+  AMP  policy: forward <= 3e-3, losses <= 5e-3 rel, gradients <= 3e-2 of max |g| (oracle run with fp16 operand rounding)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import nof_oracle as O
+from test_gpu_step import _oracle, _rel_max, amp_impl  # noqa: F401  (fixture)
+
+pytestmark = pytest.mark.gpu
+
+
+def _sm_count():
+    from bundlesdf_b200 import _lib
+    sm = C.c_int(0)
+    _lib.check(_lib.load().nof_device_info(C.byref(sm), None), 'nof_device_info')
+    return sm.value
+
+
+def _check(scene, res, ref, P, amp, scale):
+    ftol, ltol, gtol = (3e-3, 5e-3, 3e-2) if amp else (1e-4, 2e-4, 2e-3)
+    np.testing.assert_array_equal(res['valid_samples'].cpu().numpy().astype(bool), ref['valid_samples'].numpy())
+    np.testing.assert_allclose(res['weights'].cpu().numpy(), ref['weights'].detach().numpy(), rtol=1e-4, atol=1e-7)
+    assert _rel_max(res['raw'].cpu().numpy(), ref['raw'].detach().numpy()) < ftol
+    np.testing.assert_allclose(res['rgb_map'].cpu().numpy(), ref['rgb_map'].detach().numpy(), rtol=ftol * 3, atol=ftol)
+    losses = res['losses'].cpu().numpy()
+    for i, k in [(0, 'loss'), (1, 'rgb_loss'), (2, 'fs_loss'), (3, 'sdf_loss')]:
+        want = float(ref[k].detach())
+        assert abs(losses[i] - want) <= ltol * max(abs(want), 1e-6), (k, losses[i], want)
+    assert losses[5] == float(ref['valid_samples'].sum())
+    assert _rel_max(res['grad_table'].cpu().numpy() / scale, P['embeddings'].grad.numpy()) < gtol
+    for k, g in res['grad_mlp_named'].items():
+        assert _rel_max(g.cpu().numpy() / scale, P[k].grad.numpy()) < gtol, k
+    assert _rel_max(res['grad_pose'].cpu().numpy(), P['pose_data'].grad.numpy()) < gtol * 2
+    assert res['found_inf'].item() == 0
+
+
+LARGE = [
+    # name, frames, N, kwargs
+    ('C2', 12, 2048, dict(invalid_frac=0.02)),                    # 2048 rays x (64+64), L=16, T=2^19, pose on
+    ('C3', 20, 4096, dict(invalid_frac=0.02, type1_frac=0.02)),   # 4096 rays, 20-frame pool, pose noise via pose_data
+]
+
+
+@pytest.mark.parametrize('name,frames,N,kw', LARGE)
+@pytest.mark.parametrize('amp,amp_impl', [(True, 'tcgen05'), (True, 'mma'), (False, 'tcgen05')], indirect=['amp_impl'])
+def test_fused_step_at_benchmark_size(name, frames, N, kw, amp, amp_impl):
+    cfg = helpers.make_cfg(16, 256, 19, 64, 64)
+    scene = helpers.make_scene(n_frames=frames, N=N, cfg=cfg, H=240, W=320, **kw)
+    assert scene['batch'].shape[0] == N
+    sms = _sm_count()
+    assert N > 2 * sms, 'every resident CTA must walk more than one tile'       # R = 1 ray per 128-point tile at S = 128
+    rng = np.random.default_rng(17)
+    t_rand = rng.random((N, 128), dtype=np.float32)
+    res = helpers.run_fused_step(scene, amp=amp, t_rand=t_rand, loss_scale=(1024.0 if amp else None))
+    ref, P = _oracle(scene, t_rand, half=amp, z_vals=res['z_vals'].cpu())
+    _check(scene, res, ref, P, amp, 1024.0 if amp else 1.0)
+
+
+@pytest.mark.parametrize('amp_impl', ['tcgen05', 'mma'], indirect=True)
+def test_some_ctas_take_exactly_two_tiles(amp_impl):
+    """N just above the number of resident CTAs (2 per SM): most CTAs process one tile, a few come back for a second one."""
+    sms = _sm_count()
+    N = 2 * sms + 21
+    cfg = helpers.make_cfg(16, 256, 16, 64, 64)
+    scene = helpers.make_scene(n_frames=6, N=N, cfg=cfg, H=240, W=320, invalid_frac=0.05)
+    assert scene['batch'].shape[0] == N
+    t_rand = np.random.default_rng(3).random((N, 128), dtype=np.float32)
+    res = helpers.run_fused_step(scene, amp=True, t_rand=t_rand, loss_scale=1024.0)
+    ref, P = _oracle(scene, t_rand, half=True, z_vals=res['z_vals'].cpu())
+    _check(scene, res, ref, P, True, 1024.0)

@@ -22,6 +22,10 @@ def _worker(rank, world, port, q):
     dist.barrier()
     # rank r "processed" 1000 units in (1+r) seconds: whole-job value must be 2000 / 2 s
     value, t = bench.aggregate_throughput(1000, 1.0 + rank, world)
+    # bench.py's timed region: three K-step blocks; per block the MAX over ranks, the job's block time is the median over blocks
+    blocks = bench.max_over_ranks([1.0 + rank, 3.0 - rank, 1.5], world)
+    assert blocks == [2.0, 3.0, 1.5], blocks
+    assert bench.whole_job_value(1000, blocks, world) == pytest.approx(2 * 1000 / 2.0)
     q.put((rank, seed, float(seq['depths'].sum()), value, t))
     dist.barrier()
     dist.destroy_process_group()
