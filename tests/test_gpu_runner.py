@@ -228,10 +228,13 @@ def test_train_steps_blocks_match_per_step_loop():
     permutation -> same batches, same sampler ticks -> the same trajectory within the noise of the atomics."""
     ra, _ = _runner(True, n_frames=4, N=256)
     rb, _ = _runner(True, n_frames=4, N=256)
-    n = 47                                                  # 2 eager + singles up to step 10 + 10-step blocks + a tail
+    from bundlesdf_b200.nerf_runner import set_seed
+    n = 47                                                  # 2 eager + singles up to step 10 + 10-step blocks + a tail; crosses an epoch
+    set_seed(0)                                             # the mid-run reshuffle draws from the global CPU RNG: same stream for both
     for it in range(n):
         ra.train_loop(next(ra.data_loader))
         ra.global_step += 1
+    set_seed(0)
     rb.train_steps(n)
     assert rb.global_step == ra.global_step == n
     assert rb.adam_step_count.item() == ra.adam_step_count.item() == n
