@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT_DIR = os.environ.get('NOF_BUILD_DIR', os.path.join(HERE, 'lib'))     # NOF_BUILD_DIR / NOF_EXTRA_FLAGS: tuning variants
 LIB = os.path.join(OUT_DIR, 'libnof_sm100.so')
-SOURCES = ['nof_api.cu', 'nof_grid.cu', 'nof_sampling.cu', 'nof_pose.cu', 'nof_adam.cu', 'nof_step_amp.cu', 'nof_step_tc.cu', 'nof_step_f32.cu', 'nof_mesh.cu']
+SOURCES = ['nof_api.cu', 'nof_grid.cu', 'nof_sampling.cu', 'nof_pose.cu', 'nof_adam.cu', 'nof_step_amp.cu', 'nof_step_tc.cu', 'nof_step_ws.cu', 'nof_step_f32.cu', 'nof_mesh.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
          '--expt-relaxed-constexpr', '-Xptxas', '-v'] + os.environ.get('NOF_EXTRA_FLAGS', '').split()

@@ -5,6 +5,10 @@
 
 #include "nof_step_common.cuh"
 
+#ifndef NOF_AMP_IMPL_DEFAULT
+#define NOF_AMP_IMPL_DEFAULT 1
+#endif
+
 namespace nof {
 
 static thread_local char g_err[512] = "";
@@ -32,17 +36,23 @@ int step_amp_dispatch(const StepArgs& a, int NW, int blocks, cudaStream_t st);
 int step_f32_dispatch(const StepArgs& a, int blocks, cudaStream_t st);
 size_t step_tc_smem(int KE);
 int step_tc_dispatch(const StepArgs& a, int blocks, cudaStream_t st);
+size_t step_ws_smem(int KE);
+size_t step_ws_jscratch(int blocks);
+bool step_ws_tiling(int S, int* Sp_out, int* R_out);
+int step_ws_dispatch(const StepArgs& a, int blocks, cudaStream_t st);
 
-// The 128-point AMP tile has two implementations of the MLP GEMMs: tcgen05/TMEM (default) and mma.sync (NOF_AMP_IMPL=mma,
-// kept as the cross-check; larger tiles always use it).
+// The AMP step has three implementations: 2 = warp-specialised streaming pipeline on tcgen05 (nof_step_ws.cu; S <= 384; default),
+// 1 = the round-1 tcgen05 kernel (one 128-point tile per CTA iteration, S <= 128; NOF_AMP_IMPL=tc), 0 = mma.sync tiles (S <= 256;
+// NOF_AMP_IMPL=mma). 1 and 0 are kept as in-process cross-checks of 2.
 static int g_amp_impl = -1;
-static bool amp_use_tcgen05() {
+static int amp_impl() {
   if (g_amp_impl < 0) {
     const char* e = getenv("NOF_AMP_IMPL");
-    g_amp_impl = (e && strcmp(e, "mma") == 0) ? 0 : 1;
+    g_amp_impl = (e && strcmp(e, "mma") == 0) ? 0 : (e && strcmp(e, "tc") == 0) ? 1 : (e && strcmp(e, "ws") == 0) ? 2 : NOF_AMP_IMPL_DEFAULT;
   }
-  return g_amp_impl == 1;
+  return g_amp_impl;
 }
+static bool amp_use_tcgen05() { return amp_impl() == 1; }
 
 static void mlp_offsets(int E, int V, int32_t o[10], size_t* total) {
   const int sizes[10] = {64 * E, 64, 16 * 64, 16, 64 * (V + 15), 64, 64 * 64, 64, 3 * 64, 3};
@@ -85,8 +95,8 @@ using namespace nof;
 
 extern "C" int nof_version(void) { return NOF_VERSION; }
 extern "C" int nof_set_amp_impl(int impl) {
-  const int old = nof::amp_use_tcgen05() ? 1 : 0;
-  nof::g_amp_impl = impl ? 1 : 0;
+  const int old = nof::amp_impl();
+  nof::g_amp_impl = impl < 0 ? 0 : (impl > 2 ? 2 : impl);
   return old;
 }
 extern "C" const char* nof_last_error(void) { return g_err; }
@@ -133,7 +143,13 @@ extern "C" size_t nof_step_workspace_bytes(const NofStep* p) {
   int sms = 148;
   nof_device_info(&sms, nullptr);
   Tiling t;
-  if (p->amp) { if (!amp_tiling(p, sms, &t)) return 0; return kWPackBytes + (size_t)t.blocks * MAX_L * 3 * (t.NW * 32) * 4 + 256; }
+  if (p->amp) {                                             // large enough for every AMP implementation (nof_set_amp_impl may switch)
+    size_t j = 0;
+    int Sp, R;
+    if (step_ws_tiling(p->S, &Sp, &R)) j = step_ws_jscratch(std::max(1, std::min((p->N + R - 1) / R, sms)));
+    if (amp_tiling(p, sms, &t)) j = std::max(j, (size_t)t.blocks * MAX_L * 3 * (t.NW * 32) * 4);
+    return j ? kWPackBytes + j + 256 : 0;
+  }
   if (!f32_tiling(p, sms, &t)) return 0;
   return kWPackBytes + (size_t)t.blocks * MAX_L * 3 * 128 * 8 + 256;
 }
@@ -170,6 +186,13 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
   a.wpack = p->workspace;                                   // [0, kWPackBytes): packed fp16 MLP operands (tcgen05 path)
   a.jws = static_cast<char*>(p->workspace) + kWPackBytes;   // then the per-CTA Jacobian scratch
   Tiling t;
+  if (p->amp && amp_impl() == 2) {
+    int Sp, R;
+    NOF_REQUIRE(step_ws_tiling(p->S, &Sp, &R), "nof_step_fused(amp): S=%d > 384 samples per ray not supported (use amp: false)", p->S);
+    a.R = R; a.Sp = Sp; a.n_groups = (p->N + R - 1) / R;
+    NOF_REQUIRE(step_ws_smem(a.KE) <= (size_t)smem_max, "nof_step_fused(amp, ws): needs %zu B shared memory, device allows %d", step_ws_smem(a.KE), smem_max);
+    return step_ws_dispatch(a, std::max(1, std::min(a.n_groups, sms)), as_stream(stream));
+  }
   if (p->amp) {
     NOF_REQUIRE(amp_tiling(p, sms, &t), "nof_step_fused(amp): S=%d > 256 samples per ray not supported by the AMP tile (use amp: false)", p->S);
     a.R = t.R; a.Sp = t.Sp; a.n_groups = t.n_groups;

@@ -62,6 +62,9 @@ CASES = [
     (16, 256, 12, 128, 64, 18, 2, {}),                                 # reference default split 128+64, frame features on
     (4, 128, 14, 16, 16, 30, 0, {}),                                   # S=32: four rays per tile, ragged last tile
     (4, 128, 14, 24, 20, 33, 1, dict(invalid_frac=0.2)),               # S=44: padded lanes inside the tile, odd ray count, ff=1
+    (16, 256, 12, 64, 256, 11, 0, dict(invalid_frac=0.1)),             # run_custom.py:122-123 split 64+256 = 320: rays span three tiles
+    (16, 256, 12, 128, 128, 9, 1, {}),                                 # S=256: one ray = two tiles
+    (6, 128, 14, 100, 60, 13, 0, {}),                                  # S=160 (padded to 192 lanes per ray), L=6 (operand width padded to 16)
 ]
 
 
@@ -70,16 +73,18 @@ def amp_impl(request):
     """Select the AMP tile implementation through the C ABI (include/nof.h nof_set_amp_impl) and restore it afterwards."""
     from bundlesdf_b200 import _lib
     lib = _lib.load()
-    old = lib.nof_set_amp_impl(1 if request.param == 'tcgen05' else 0)
+    old = lib.nof_set_amp_impl({'mma': 0, 'tcgen05': 1, 'ws': 2}[request.param])
     yield request.param
     lib.nof_set_amp_impl(old)
 
 
 @pytest.mark.parametrize('L,finest,log2T,S_occ,S_d,N,ff,kw', CASES)
-@pytest.mark.parametrize('amp,amp_impl', [(False, 'tcgen05'), (True, 'tcgen05'), (True, 'mma')], indirect=['amp_impl'])
+@pytest.mark.parametrize('amp,amp_impl', [(False, 'tcgen05'), (True, 'ws'), (True, 'tcgen05'), (True, 'mma')], indirect=['amp_impl'])
 def test_fused_step_matches_oracle(L, finest, log2T, S_occ, S_d, N, ff, kw, amp, amp_impl):
     if amp and amp_impl == 'mma' and S_occ + S_d > 128:
-        pytest.skip('S > 128 always runs the mma.sync tile: covered by the tcgen05-default case')
+        pytest.skip('S > 128 always runs the mma.sync tile: covered by the tcgen05 (round-1 kernel) case')
+    if amp and amp_impl != 'ws' and S_occ + S_d > 256:
+        pytest.skip('S > 256 is carried by the streaming kernel only')
     cfg = helpers.make_cfg(L, finest, log2T, S_occ, S_d, ff=ff)
     if ff:
         cfg['fs_rgb_weight'] = 0.5

@@ -53,7 +53,7 @@ LARGE = [
 
 
 @pytest.mark.parametrize('name,frames,N,kw', LARGE)
-@pytest.mark.parametrize('amp,amp_impl', [(True, 'tcgen05'), (True, 'mma'), (False, 'tcgen05')], indirect=['amp_impl'])
+@pytest.mark.parametrize('amp,amp_impl', [(True, 'ws'), (True, 'tcgen05'), (True, 'mma'), (False, 'tcgen05')], indirect=['amp_impl'])
 def test_fused_step_at_benchmark_size(name, frames, N, kw, amp, amp_impl):
     cfg = helpers.make_cfg(16, 256, 19, 64, 64)
     scene = helpers.make_scene(n_frames=frames, N=N, cfg=cfg, H=240, W=320, **kw)
@@ -67,11 +67,11 @@ def test_fused_step_at_benchmark_size(name, frames, N, kw, amp, amp_impl):
     _check(scene, res, ref, P, amp, 1024.0 if amp else 1.0)
 
 
-@pytest.mark.parametrize('amp_impl', ['tcgen05', 'mma'], indirect=True)
+@pytest.mark.parametrize('amp_impl', ['ws', 'tcgen05', 'mma'], indirect=True)
 def test_some_ctas_take_exactly_two_tiles(amp_impl):
     """N just above the number of resident CTAs (2 per SM): most CTAs process one tile, a few come back for a second one."""
     sms = _sm_count()
-    N = 2 * sms + 21
+    N = (1 if amp_impl == 'ws' else 2) * sms + 21         # the streaming kernel runs one CTA per SM, the others two
     cfg = helpers.make_cfg(16, 256, 16, 64, 64)
     scene = helpers.make_scene(n_frames=6, N=N, cfg=cfg, H=240, W=320, invalid_frac=0.05)
     assert scene['batch'].shape[0] == N
