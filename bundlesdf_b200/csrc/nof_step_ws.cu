@@ -35,7 +35,7 @@ constexpr int NW_EPI = 8, NW_WG = 4, NW_GA = 4, NW_SC = 4;
 constexpr int W_EPI0 = 0, W_WG0 = 8, W_GA0 = 12, W_SC0 = 16, W_MMA = 20;
 constexpr int NT = 24 * 32;                   // six warpgroups; the last one holds the MMA issuer and three parked warps
 constexpr int BAR_EPI = 1, BAR_GA = 2, BAR_SC = 3;
-constexpr int REG_EPI = 80, REG_WG = 104, REG_GA = 120, REG_SC = 72, REG_MISC = 24;    // 768 threads x 80 registers re-dealt per role
+constexpr int REG_EPI = 80, REG_WG = 104, REG_GA = 104, REG_SC = 72, REG_MISC = 40;    // 768 threads x 80 registers re-dealt per role
 
 enum { Q_START = 1, Q_END = 2 };
 
@@ -65,7 +65,16 @@ struct TileHdr {
 struct Plan {
   int w1, w2, w3g, w4, w5, bias, w3v, lv, img_bytes;          // operand image (one TMA bulk copy)
   int slot0, slot_bytes, x0, x1, xg, x3, x4, zs, out, hdr;    // slot-relative offsets
-  int d_o, rays, bars, misc, total;
+  int d_o, rays, bars, misc, gtab, total;
+};
+struct GemmTab {                               // one chained GEMM as the MMA issuer needs it (built once per CTA)
+  uint32_t a_off;                              // A operand: byte offset inside the tile slot, or absolute (a_abs) shared-memory address
+  uint32_t a_abs;
+  uint32_t a_hi;                               // high word of the A descriptor (SBO, version)
+  uint32_t b_lo, b_hi;                         // B descriptor for k-step 0
+  uint32_t b_step;                             // added to b_lo per k-step
+  uint32_t idesc;
+  uint32_t nks;
 };
 __host__ __device__ inline Plan make_plan(int KE) {
   Plan s;
@@ -76,7 +85,7 @@ __host__ __device__ inline Plan make_plan(int KE) {
   s.w3g = take(64 * KG * 2);
   s.w4 = take(64 * 64 * 2);
   s.w5 = take(16 * 64 * 2);
-  s.bias = take(216 * 4);                     // b1 64 | b2 16 | b3 64 | b4 64 | b5 8
+  s.bias = take(280 * 4);                     // b1 64 | b2 16 | b3 64 | b4 64 | b5 8 | 64 zeros (the 'no per-ray bias' vector)
   s.w3v = take(64 * VPAD * 2);
   s.lv = take((int)sizeof(LevelS));
   s.img_bytes = o;
@@ -97,6 +106,7 @@ __host__ __device__ inline Plan make_plan(int KE) {
   s.rays = take(NRAY * (int)sizeof(RayW));
   s.bars = take(24 * 8);
   s.misc = take(64);
+  s.gtab = take(10 * (int)sizeof(GemmTab));
   s.total = o;
   return s;
 }
@@ -109,6 +119,7 @@ enum { B_IMG = 0, B_MMA = 1, B_OPND = 2, B_WGD = 3, B_GFULL = 4, B_SFREE = 7, B_
 struct PhaseWaiter {
   uint32_t seen;
   __device__ __forceinline__ bool until(uint64_t* bar, uint32_t need, volatile int* abort_flag) {
+#pragma unroll 1
     while (seen < need) {
       if (!mbar_wait(bar, seen & 1u, abort_flag)) return false;
       ++seen;
@@ -278,15 +289,16 @@ struct Seq {
 };
 
 // wgrad on mma.sync reading core-matrix buffers: dW[strip*16..+16][nt0*8 .. +NTU*8) += dY^T X over the 128 points of the tile.
-// QSUM: also return the column sums of dY per 32-row quadrant (c[q][0..1] for rows g8, g8+8 of the strip; lanes with t4 == 0).
+// QSUM: the column sums of dY per 32-row quadrant (rows g8, g8+8 of the strip; lanes with t4 == 0) are added to cr of the quadrant's ray.
 template <int NTU, bool QSUM>
 __device__ __forceinline__ void wgrad_item(uint32_t dY, int Ky, uint32_t X, int Kx, int strip, int nt0, float (*acc)[4], float* bias2, bool do_bias,
-                                           int lane, float (*qs)[2]) {
+                                           int lane, RayW* rays, const TileHdr* hdr) {
   const uint32_t ones = 0x3C003C00u;
   const int pa = (lane & 7) + (lane >> 4) * 8, oa = strip * 16 + ((lane >> 3) & 1) * 8;       // A: rows p, cols o (dY^T)
   const int pb = (lane & 7) + ((lane >> 3) & 1) * 8, ib = (lane >> 4) * 8;                      // B: rows p, cols i
 #pragma unroll
   for (int q = 0; q < 4; ++q) {                                  // the tile's four 32-row quadrants, two k-steps each
+    float q0 = 0.f, q1 = 0.f;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int ks = 2 * q + h;
@@ -302,10 +314,16 @@ __device__ __forceinline__ void wgrad_item(uint32_t dY, int Ky, uint32_t X, int 
       if (do_bias) {
         float t[4] = {0.f, 0.f, 0.f, 0.f};
         mma16816(t, af, ones, ones);
-        bias2[0] += t[0];
-        bias2[1] += t[2];
-        if (QSUM) { qs[q][0] += t[0]; qs[q][1] += t[2]; }
+        q0 += t[0];
+        q1 += t[2];
       }
+    }
+    bias2[0] += q0;
+    bias2[1] += q1;
+    if (QSUM && (lane & 3) == 0) {
+      RayW& rq = rays[hdr->qray[q]];
+      if (q0 != 0.f) atomicAdd(&rq.cr[strip * 16 + (lane >> 2)], q0);
+      if (q1 != 0.f) atomicAdd(&rq.cr[strip * 16 + (lane >> 2) + 8], q1);
     }
   }
 }
@@ -359,7 +377,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, int
 __device__ __forceinline__ bool h2_bad(uint32_t w) { return ((w & 0x7C00u) == 0x7C00u) || ((w & 0x7C000000u) == 0x7C000000u); }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int KE_>
+template <int KE_, bool POSE>
 __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
   constexpr int KE = KE_;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -417,11 +435,17 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
   __syncthreads();
 
   auto slot_ptr = [&](int t) { return smem + sp.slot0 + (t % NS) * sp.slot_bytes; };
+#ifdef NOF_WS_PROF   // role profile of CTA 0: cycles each warp spends waiting on mbarriers vs its whole role loop (profiles/ws_roles.py)
+  long long prof_wait = 0, prof_t0 = clock64();
+#define WS_WAIT(expr) do { const long long _t = clock64(); expr; prof_wait += clock64() - _t; } while (0)
+#else
+#define WS_WAIT(expr) do { expr; } while (0)
+#endif
   // role-internal barrier over `bar` (count = warps of the role)
   auto role_sync = [&](uint64_t* bar, uint32_t& phase) {
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);
-    ok &= mbar_wait(bar, phase & 1u, s_abort);
+    WS_WAIT(ok &= mbar_wait(bar, phase & 1u, s_abort));
     ++phase;
   };
   int* tile_ticket = reinterpret_cast<int*>(static_cast<char*>(a.wpack) + kWPackBytes - 16);
@@ -441,7 +465,7 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
       for (int j = 0; j < (last ? 1 : G); ++j, ++t) {
         unsigned char* sl = slot_ptr(t);
         TileHdr* hdr = reinterpret_cast<TileHdr*>(sl + sp.hdr);
-        ok &= mbar_wait(&bars[B_SFREE + t % NS], ((uint32_t)(t / NS) & 1u) ^ 1u, s_abort);
+        WS_WAIT(ok &= mbar_wait(&bars[B_SFREE + t % NS], ((uint32_t)(t / NS) & 1u) ^ 1u, s_abort));
         if (last) {
           if (gq == 0 && lane == 0) hdr->grp = -1;
           break;
@@ -492,18 +516,19 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
           uint32_t w[4] = {0u, 0u, 0u, 0u};
           if (valid) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int l = 4 * c + k;
-              if (l < L) {
-                float enc[2], J[3][2];
-                if (a.p.need_pose_grad) {
-                  gather_level<true, true>(a.p.table_f16, lv, l, u, enc, J);
+            for (int k2 = 0; k2 < 2; ++k2) {                     // two levels in flight (16 loads), twice
 #pragma unroll
-                  for (int d = 0; d < 3; ++d) Jslot[(size_t)(l * 3 + d) * PT + row] = __floats2half2_rn(J[d][0], J[d][1]);
-                } else {
-                  gather_level<true, false>(a.p.table_f16, lv, l, u, enc, J);
+              for (int k1 = 0; k1 < 2; ++k1) {
+                const int k = 2 * k2 + k1, l = 4 * c + k;
+                if (l < L) {
+                  float enc[2], J[3][2];
+                  gather_level<true, POSE>(a.p.table_f16, lv, l, u, enc, J);
+                  if (POSE) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) Jslot[(size_t)(l * 3 + d) * PT + row] = __floats2half2_rn(J[d][0], J[d][1]);
+                  }
+                  w[k] = pack_h2(enc[0], enc[1]);
                 }
-                w[k] = pack_h2(enc[0], enc[1]);
               }
             }
           }
@@ -531,7 +556,7 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
     for (int t = 0;; ++t) {
       unsigned char* sl = slot_ptr(t);
       const TileHdr* hdr = reinterpret_cast<const TileHdr*>(sl + sp.hdr);
-      ok &= mbar_wait(&bars[B_SFULL + t % NS], (uint32_t)(t / NS) & 1u, s_abort);
+      WS_WAIT(ok &= mbar_wait(&bars[B_SFULL + t % NS], (uint32_t)(t / NS) & 1u, s_abort));
       if (!ok || hdr->grp < 0) break;
       const float* zs = reinterpret_cast<const float*>(sl + sp.zs);
       const float* dEb = reinterpret_cast<const float*>(sl + sp.x3);
@@ -571,7 +596,7 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
                 pg[d] = (uint32_t)fl;
                 fr[d] = pp - fl;
               }
-              if (a.p.need_pose_grad) {
+              if (POSE) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                   const float2 jj = __half22float2(Jslot[(size_t)(l * 3 + d) * PT + p0 + j]);
@@ -608,7 +633,7 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
           }
         }
       }
-      if (a.p.need_pose_grad) {
+      if (POSE) {
         // x = R (dir z) + t  =>  dL/dR[i][j] = dir[j] * sum gi z ,  dL/dt[i] = sum gi. Lanes of one quadrant (4 sample groups x 2 levels) first
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -623,7 +648,7 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
       // rays whose last samples are in this tile: pose / frame-feature gradients. Warp sw looks after quadrant sw.
       if (hdr->qflags[sw] & Q_END) {
         RayW& r2 = rays[hdr->qray[sw]];
-        if (r2.active && (a.p.grad_feat || (a.p.need_pose_grad && r2.frame != 0))) {
+        if (r2.active && (a.p.grad_feat || (POSE && r2.frame != 0))) {
           float dv[MAX_V];
           const float c0 = r2.cr[lane], c1 = r2.cr[lane + 32];
 #pragma unroll
@@ -636,7 +661,7 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
             if (a.p.grad_feat)
               for (int j = 0; j < a.p.ff; ++j)
                 if (dv[j] != 0.f) red_add(a.p.grad_feat + (size_t)r2.frame * a.p.ff + j, dv[j]);
-            if (a.p.need_pose_grad && r2.frame != 0) {
+            if (POSE && r2.frame != 0) {
               float gd[3];
               sh3_backward(r2.dw, dv + a.p.ff, gd);
 #pragma unroll
@@ -680,24 +705,15 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
         const TileHdr* hdr = reinterpret_cast<const TileHdr*>(sl + sp.hdr);
         const uint32_t sa = smem_u32(sl);
         const uint32_t aX0 = sa + sp.x0, aX1 = sa + sp.x1, aXG = sa + sp.xg, aX3 = sa + sp.x3, aX4 = sa + sp.x4;
-        ok &= pdy.until(&bars[B_DY], ++nd, s_abort);                      // dOut ready (seeds)
-        wgrad_item<2, false>(aDO, KG, aX4, 64, 0, 2 * ww, wg5, wb5, ww == 0, lane, nullptr);
+        WS_WAIT(ok &= pdy.until(&bars[B_DY], ++nd, s_abort));                      // dOut ready (seeds)
+        wgrad_item<2, false>(aDO, KG, aX4, 64, 0, 2 * ww, wg5, wb5, ww == 0, lane, rays, hdr);
         wg_done();
-        ok &= pdy.until(&bars[B_DY], ++nd, s_abort);                // dY4 ready
-        wgrad_item<8, false>(aX4, 64, aX3, 64, ww, 0, wg4, wb4, true, lane, nullptr);
+        WS_WAIT(ok &= pdy.until(&bars[B_DY], ++nd, s_abort));                // dY4 ready
+        wgrad_item<8, false>(aX4, 64, aX3, 64, ww, 0, wg4, wb4, true, lane, rays, hdr);
         wg_done();
-        ok &= pdy.until(&bars[B_DY], ++nd, s_abort);                // dY3 ready
+        WS_WAIT(ok &= pdy.until(&bars[B_DY], ++nd, s_abort));                // dY3 ready
         {
-          float qs[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-          wgrad_item<2, true>(aX3, 64, aXG, KG, ww, 0, wg3, wb3, true, lane, qs);
-          if (t4 == 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              RayW& rq = rays[hdr->qray[q]];
-              if (qs[q][0] != 0.f) atomicAdd(&rq.cr[ww * 16 + g8], qs[q][0]);
-              if (qs[q][1] != 0.f) atomicAdd(&rq.cr[ww * 16 + g8 + 8], qs[q][1]);
-            }
-          }
+          wgrad_item<2, true>(aX3, 64, aXG, KG, ww, 0, wg3, wb3, true, lane, rays, hdr);
           __syncwarp();
 #pragma unroll 1
           for (int q = 0; q < 4; ++q) {                          // rays complete in this tile: dW3[:, views] += c_r (x) views
@@ -712,17 +728,17 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
           }
         }
         wg_done();
-        ok &= pdy.until(&bars[B_DY], ++nd, s_abort);                // dH2 ready
-        wgrad_item<2, false>(aDO, KG, aX1, 64, 0, 2 * ww, wg2, wb2, ww == 0, lane, nullptr);
+        WS_WAIT(ok &= pdy.until(&bars[B_DY], ++nd, s_abort));                // dH2 ready
+        wgrad_item<2, false>(aDO, KG, aX1, 64, 0, 2 * ww, wg2, wb2, ww == 0, lane, rays, hdr);
         wg_done();
-        ok &= pdy.until(&bars[B_DY], ++nd, s_abort);                // dY1 ready
-        wgrad_item<KE / 8, false>(aX1, 64, aX0, KE, ww, 0, wg1, wb1, true, lane, nullptr);
+        WS_WAIT(ok &= pdy.until(&bars[B_DY], ++nd, s_abort));                // dY1 ready
+        wgrad_item<KE / 8, false>(aX1, 64, aX0, KE, ww, 0, wg1, wb1, true, lane, rays, hdr);
         wg_done();
         if (lane == 0) mbar_arrive(&bars[B_SFREE + t % NS]);    // this role no longer reads the slot
         ++seq.b;
       } else if (!seq.done) {
         const int t = seq.f;
-        ok &= mbar_wait(&bars[B_GFULL + t % NS], (uint32_t)(t / NS) & 1u, s_abort);
+        WS_WAIT(ok &= mbar_wait(&bars[B_GFULL + t % NS], (uint32_t)(t / NS) & 1u, s_abort));
         if (reinterpret_cast<const TileHdr*>(slot_ptr(t) + sp.hdr)->grp < 0) seq.done = true;
         else ++seq.f;
       } else {
@@ -748,43 +764,69 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
     // ================================================================================== MMA issuer (one thread; three parked warps)
     reg_dec<REG_MISC>();
     if (warp == W_MMA && lane == 0) {
+      // The ten GEMMs of a tile as a table: F1..F5 (forward, B = W^T K-major), B5..B1 (dgrad, B = W as MN-major view). The issue loop below
+      // is a few dozen instructions: this thread runs rarely and must not drag kilobytes of code through the instruction cache every time.
+      GemmTab* gt = reinterpret_cast<GemmTab*>(smem + sp.gtab);
+      {
+        auto fill = [&](int i, uint32_t a_off, uint32_t a_abs, int KA, uint32_t b_addr, int KB, int N, int K, int b_mn) {
+          GemmTab g;
+          g.a_off = a_off; g.a_abs = a_abs;
+          const uint64_t ad = umma_desc(0, 128, KA * 16);
+          g.a_hi = (uint32_t)(ad >> 32);
+          const uint64_t bd = b_mn ? umma_desc(b_addr, KB * 16, 128) : umma_desc(b_addr, 128, KB * 16);
+          g.b_lo = (uint32_t)bd; g.b_hi = (uint32_t)(bd >> 32);
+          g.b_step = b_mn ? (uint32_t)(2 * KB) : 16u;             // per k-step of 16: two 8-row groups of an MN-major buffer, or 256 bytes of a K-major one (>> 4)
+          g.idesc = umma_idesc(128, N, 0, b_mn);
+          g.nks = (uint32_t)(K / 16);
+          gt[i] = g;
+        };
+        fill(0, sp.x0, 0, KE, aW1, KE, 64, KE, 0);
+        fill(1, sp.x1, 0, 64, aW2, 64, 16, 64, 0);
+        fill(2, sp.xg, 0, KG, aW3, KG, 64, KG, 0);
+        fill(3, sp.x3, 0, 64, aW4, 64, 64, 64, 0);
+        fill(4, sp.x4, 0, 64, aW5, 64, 16, 64, 0);
+        fill(5, 0, aDO, KG, aW5, 64, 64, 16, 1);
+        fill(6, sp.x4, 0, 64, aW4, 64, 64, 64, 1);
+        fill(7, sp.x3, 0, 64, aW3, KG, KG, 64, 1);
+        fill(8, 0, aDO, KG, aW2, 64, 64, 16, 1);
+        fill(9, sp.x1, 0, 64, aW1, KE, KE, 64, 1);
+      }
       Seq seq{0, 0, G, Sp, false};
-      int ec = 0;
-      uint64_t* bm = &bars[B_MMA];
+      uint32_t ec = 0;
       PhaseWaiter pw{0};
-      auto wait_step = [&]() {                                   // every EPILOG step that precedes the next GEMM is complete
-        ok &= pw.until(&bars[B_OPND], (uint32_t)ec, s_abort);
-        tc_fence_after();
-      };
       while (ok) {
+        int g0, t;
         if (seq.can_b()) {
-          const uint32_t sa = smem_u32(slot_ptr(seq.b));
-          const uint32_t aX1 = sa + sp.x1, aX3 = sa + sp.x3, aX4 = sa + sp.x4;
-          ec += 1;                                               // the seeds step
-          wait_step(); issue_gemm<64, 16, 1>(tmem, aDO, KG, aW5, 64, bm); ++ec;
-          wait_step(); issue_gemm<64, 64, 1>(tmem, aX4, 64, aW4, 64, bm); ++ec;
-          wait_step(); issue_gemm<KG, 64, 1>(tmem, aX3, 64, aW3, KG, bm); ++ec;
-          wait_step(); issue_gemm<64, 16, 1>(tmem, aDO, KG, aW2, 64, bm); ++ec;
-          wait_step(); issue_gemm<KE, 64, 1>(tmem, aX1, 64, aW1, KE, bm); ++ec;
-          wait_step();                                           // observe the op's last step too: no phase of B_OPND is ever skipped
-          ++seq.b;
+          t = seq.b++;
+          g0 = 5;
+          ec += 1;                                               // the seeds step precedes the first dgrad
         } else if (!seq.done) {
-          const int t = seq.f;
-          ok &= mbar_wait(&bars[B_GFULL + t % NS], (uint32_t)(t / NS) & 1u, s_abort);
+          t = seq.f;
+          WS_WAIT(ok &= mbar_wait(&bars[B_GFULL + t % NS], (uint32_t)(t / NS) & 1u, s_abort));
           if (reinterpret_cast<const TileHdr*>(slot_ptr(t) + sp.hdr)->grp < 0) { seq.done = true; continue; }
-          const uint32_t sa = smem_u32(slot_ptr(t));
-          const uint32_t aX0 = sa + sp.x0, aX1 = sa + sp.x1, aXG = sa + sp.xg, aX3 = sa + sp.x3, aX4 = sa + sp.x4;
-          wait_step();
-          issue_gemm<64, KE, 0>(tmem, aX0, KE, aW1, KE, bm); ++ec;
-          wait_step(); issue_gemm<16, 64, 0>(tmem, aX1, 64, aW2, 64, bm); ++ec;
-          wait_step(); issue_gemm<64, KG, 0>(tmem, aXG, KG, aW3, KG, bm); ++ec;
-          wait_step(); issue_gemm<64, 64, 0>(tmem, aX3, 64, aW4, 64, bm); ++ec;
-          wait_step(); issue_gemm<16, 64, 0>(tmem, aX4, 64, aW5, 64, bm); ++ec;
-          wait_step();
           ++seq.f;
+          g0 = 0;
         } else {
           break;
         }
+        const uint32_t sa = smem_u32(slot_ptr(t));
+#pragma unroll 1
+        for (int g = g0; g < g0 + 5; ++g) {
+          WS_WAIT(ok &= pw.until(&bars[B_OPND], ec, s_abort));   // every EPILOG step that precedes this GEMM is complete
+          tc_fence_after();
+          const GemmTab G_ = gt[g];
+          const uint32_t a_addr = G_.a_abs ? G_.a_abs : sa + G_.a_off;
+          uint32_t a_lo = ((a_addr >> 4) & 0x3FFFu) | (8u << 16), b_lo = G_.b_lo;      // LBO = 128 bytes
+#pragma unroll 1
+          for (uint32_t ks = 0; ks < G_.nks; ++ks) {
+            umma_f16(tmem, ((uint64_t)G_.a_hi << 32) | a_lo, ((uint64_t)G_.b_hi << 32) | b_lo, G_.idesc, ks);
+            a_lo += 16u;                                         // 256 bytes further along K
+            b_lo += G_.b_step;
+          }
+          umma_commit(&bars[B_MMA]);
+          ++ec;
+        }
+        WS_WAIT(ok &= pw.until(&bars[B_OPND], ec, s_abort));     // observe the op's last step too: no phase of B_OPND is ever skipped
       }
     }
     __syncwarp();
@@ -800,7 +842,7 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
     float n_valid_s = 0.f, n_valid_r = 0.f;
     bool overflow = false;
     auto mma_wait = [&]() {
-      ok &= mbar_wait(&bars[B_MMA], gc & 1u, s_abort);
+      WS_WAIT(ok &= mbar_wait(&bars[B_MMA], gc & 1u, s_abort));
       ++gc;
       tc_fence_after();
     };
@@ -823,8 +865,7 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = half * 32 + ch * 8 + 2 * j;
-          float x0 = v[ch * 8 + 2 * j] + bias[c], x1 = v[ch * 8 + 2 * j + 1] + bias[c + 1];
-          if (rb) { x0 += rb[c]; x1 += rb[c + 1]; }
+          const float x0 = v[ch * 8 + 2 * j] + bias[c] + rb[c], x1 = v[ch * 8 + 2 * j + 1] + bias[c + 1] + rb[c + 1];
           w[j] = pack_h2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
         }
         *reinterpret_cast<uint4*>(pX + cm_off(row, half * 32 + ch * 8, 64)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -834,7 +875,7 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
     auto bwd_mask_store = [&](unsigned char* pX, uint32_t wg_need) {
       float v[32];
       TmemLd<32>::ld(trow + half * 32, v);
-      ok &= pwg.until(&bars[B_WGD], wg_need, s_abort);           // the weight-gradient warps are done reading this activation
+      WS_WAIT(ok &= pwg.until(&bars[B_WGD], wg_need, s_abort));           // the weight-gradient warps are done reading this activation
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         unsigned char* p = pX + cm_off(row, half * 32 + ch * 8, 64);
@@ -862,7 +903,7 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
         const int sidx = hdr->qs0[quad] + lane;
         const bool active = rs.active && sidx < S;
         role_sync(&bars[B_REP], rph);                                // every EPILOG warp's compositing sums of the forwarded tiles are in
-        ok &= pwg.until(&bars[B_WGD], wc, s_abort);              // (observe the previous backward's last weight-gradient phase)
+        WS_WAIT(ok &= pwg.until(&bars[B_WGD], wc, s_abort));              // (observe the previous backward's last weight-gradient phase)
         float dsdf_s = 0.f;
         if (owner) {
           const float* zs = reinterpret_cast<const float*>(sl + sp.zs);
@@ -902,44 +943,36 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
           *reinterpret_cast<uint4*>(pDO + cm_off(row, 8, KG)) = make_uint4(0u, 0u, 0u, 0u);
         }
         step_done(true);                                          // dOut visible
-        // ---- layer 5: dY4 over X4 (wgrad5 has read X4)
-        mma_wait();
-        bwd_mask_store(sl + sp.x4, wc + 1);
-        step_done(true);
-        // ---- layer 4: dY3 over X3 (wgrad4 has read X3)
-        mma_wait();
-        bwd_mask_store(sl + sp.x3, wc + 2);
-        step_done(true);
-        // ---- layer 3: d geo (15) -> dH2[1..15], dH2[0] = d sdf
-        mma_wait();
-        {
-          float v[8];
-          TmemLd<8>::ld(trow + half * 8, v);
+#pragma unroll 1
+        for (int ly = 0; ly < 5; ++ly) {                          // layers 5, 4, 3, 2, 1
+          mma_wait();
+          if (ly == 2) {
+            // ---- layer 3: d geo (15) -> dH2[1..15], dH2[0] = d sdf
+            float v[8];
+            TmemLd<8>::ld(trow + half * 8, v);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = half * 8 + j;
-            if (col < 15) {
-              overflow |= !(fabsf(v[j]) <= 65504.f);
-              *reinterpret_cast<__half*>(pDO + cm_off(row, 1 + col, KG)) = __float2half_rn(v[j]);
+            for (int j = 0; j < 8; ++j) {
+              const int col = half * 8 + j;
+              if (col < 15) {
+                overflow |= !(fabsf(v[j]) <= 65504.f);
+                *reinterpret_cast<__half*>(pDO + cm_off(row, 1 + col, KG)) = __float2half_rn(v[j]);
+              }
             }
-          }
-          if (owner) *reinterpret_cast<__half*>(pDO + cm_off(row, 0, KG)) = __float2half_rn(dsdf_s);
-        }
-        ok &= pwg.until(&bars[B_WGD], wc + 3, s_abort);          // every phase of a barrier must be observed before the next one can complete
-        step_done(true);
-        // ---- layer 2: dY1 over X1 (wgrad2 has read X1; wgrad3 / wgrad4 are done with X3 / X4, which dEnc overwrites next)
-        mma_wait();
-        bwd_mask_store(sl + sp.x1, wc + 4);
-        step_done(true);
-        // ---- layer 1: dEnc fp32, transposed [column][DES], over X3|X4 (dead)
-        mma_wait();
-        {
-          constexpr int NH = KE / 2;
-          float v[NH];
-          TmemLd<NH>::ld(trow + half * NH, v);
-          float* dE = reinterpret_cast<float*>(sl + sp.x3) + des_idx(row);
+            if (owner) *reinterpret_cast<__half*>(pDO + cm_off(row, 0, KG)) = __float2half_rn(dsdf_s);
+            WS_WAIT(ok &= pwg.until(&bars[B_WGD], wc + 3, s_abort));      // every phase of a barrier must be observed before the next one can complete
+          } else if (ly == 4) {
+            // ---- layer 1: dEnc fp32, transposed [column][DES], over X3|X4 (dead: wgrad3 / wgrad4 were observed done at layer 2)
+            constexpr int NH = KE / 2;
+            float v[NH];
+            TmemLd<NH>::ld(trow + half * NH, v);
+            float* dE = reinterpret_cast<float*>(sl + sp.x3) + des_idx(row);
 #pragma unroll
-          for (int j = 0; j < NH; ++j) dE[(half * NH + j) * DES] = v[j];
+            for (int j = 0; j < NH; ++j) dE[(half * NH + j) * DES] = v[j];
+          } else {
+            // ---- layers 5, 4, 2: dY over the stored activation (X4, X3, X1) once the weight-gradient warps have read it
+            bwd_mask_store(sl + (ly == 0 ? sp.x4 : ly == 1 ? sp.x3 : sp.x1), wc + (ly == 0 ? 1u : ly == 1 ? 2u : 4u));
+          }
+          if (ly < 4) step_done(true);
         }
         wc += 5;
         tc_fence_before();
@@ -953,60 +986,53 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
         // ---------------------------------------------------------------- forward of tile seq.f
         const int t = seq.f;
         unsigned char* sl = slot_ptr(t);
-        ok &= mbar_wait(&bars[B_GFULL + t % NS], (uint32_t)(t / NS) & 1u, s_abort);
+        WS_WAIT(ok &= mbar_wait(&bars[B_GFULL + t % NS], (uint32_t)(t / NS) & 1u, s_abort));
         const TileHdr* hdr = reinterpret_cast<const TileHdr*>(sl + sp.hdr);
         if (hdr->grp < 0) { seq.done = true; continue; }
         RayW& rs = rays[hdr->qray[quad]];
         const bool valid = (hdr->qvalid[quad] >> lane) & 1u;
-        // L1: E -> 64, ReLU
-        mma_wait();
-        fwd_relu_store(sl + sp.x1, sB, nullptr);
-        step_done(false);
-        // L2: 64 -> 16 (sdf | geo 15)
-        mma_wait();
-        {
-          float v[8];
-          TmemLd<8>::ld(trow + half * 8, v);
-          unsigned char* pXG = sl + sp.xg;
+#pragma unroll 1
+        for (int ly = 0; ly < 5; ++ly) {
+          mma_wait();
+          if (ly == 1) {
+            // L2: 64 -> 16 (sdf | geo 15)
+            float v[8];
+            TmemLd<8>::ld(trow + half * 8, v);
+            unsigned char* pXG = sl + sp.xg;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = half * 8 + j;
-            const __half hv = __float2half_rn(v[j] + sB[64 + col]);
-            if (col == 0) *reinterpret_cast<__half*>(sl + sp.out + row * 8 + 6) = hv;
-            else *reinterpret_cast<__half*>(pXG + cm_off(row, col - 1, KG)) = hv;
+            for (int j = 0; j < 8; ++j) {
+              const int col = half * 8 + j;
+              const __half hv = __float2half_rn(v[j] + sB[64 + col]);
+              if (col == 0) *reinterpret_cast<__half*>(sl + sp.out + row * 8 + 6) = hv;
+              else *reinterpret_cast<__half*>(pXG + cm_off(row, col - 1, KG)) = hv;
+            }
+            if (!owner) *reinterpret_cast<__half*>(pXG + cm_off(row, 15, KG)) = __float2half_rn(0.f);
+          } else if (ly == 4) {
+            // L5: 64 -> 3; compositing partial sums of this quadrant
+            if (owner) {
+              float v[8];
+              TmemLd<8>::ld(trow, v);
+              const float w_raw = reinterpret_cast<const float*>(sl + sp.zs)[DES + des_idx(row)];
+              __half h[3];
+              float pr[3];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                h[c] = __float2half_rn(v[c] + sB[208 + c]);
+                pr[c] = warp_sum(valid ? w_raw * sigmoidf_(__half2float(h[c])) : 0.f);
+              }
+              *reinterpret_cast<__half2*>(sl + sp.out + row * 8) = __halves2half2(h[0], h[1]);
+              *reinterpret_cast<__half*>(sl + sp.out + row * 8 + 4) = h[2];
+              if (lane == 0 && (pr[0] != 0.f || pr[1] != 0.f || pr[2] != 0.f)) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) atomicAdd(&rs.rgbacc[c], pr[c]);
+              }
+            }
+          } else {
+            // L1 (E -> 64), L3 (geo 15 + the ray's view/feature share as a bias -> 64), L4 (64 -> 64): ReLU -> next operand
+            fwd_relu_store(sl + (ly == 0 ? sp.x1 : ly == 2 ? sp.x3 : sp.x4), sB + (ly == 0 ? 0 : ly == 2 ? 80 : 144), ly == 2 ? rs.vb : sB + 216);
           }
-          if (!owner) *reinterpret_cast<__half*>(pXG + cm_off(row, 15, KG)) = __float2half_rn(0.f);
+          step_done(false);
         }
-        step_done(false);
-        // L3: geo 15 (+ the ray's view/feature share as a bias) -> 64, ReLU
-        mma_wait();
-        fwd_relu_store(sl + sp.x3, sB + 80, rs.vb);
-        step_done(false);
-        // L4: 64 -> 64, ReLU
-        mma_wait();
-        fwd_relu_store(sl + sp.x4, sB + 144, nullptr);
-        step_done(false);
-        // L5: 64 -> 3; compositing partial sums of this quadrant
-        mma_wait();
-        if (owner) {
-          float v[8];
-          TmemLd<8>::ld(trow, v);
-          const float w_raw = reinterpret_cast<const float*>(sl + sp.zs)[DES + des_idx(row)];
-          __half h[3];
-          float pr[3];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            h[c] = __float2half_rn(v[c] + sB[208 + c]);
-            pr[c] = warp_sum(valid ? w_raw * sigmoidf_(__half2float(h[c])) : 0.f);
-          }
-          *reinterpret_cast<__half2*>(sl + sp.out + row * 8) = __halves2half2(h[0], h[1]);
-          *reinterpret_cast<__half*>(sl + sp.out + row * 8 + 4) = h[2];
-          if (lane == 0 && (pr[0] != 0.f || pr[1] != 0.f || pr[2] != 0.f)) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) atomicAdd(&rs.rgbacc[c], pr[c]);
-          }
-        }
-        step_done(false);
         ++seq.f;
       } else {
         break;
@@ -1028,6 +1054,13 @@ __global__ void __launch_bounds__(NT, 1) step_ws_kernel(const StepArgs a) {
     }
   }
 
+#ifdef NOF_WS_PROF
+  if (blockIdx.x == 0 && lane == 0) {
+    long long* pr = reinterpret_cast<long long*>(static_cast<char*>(a.wpack) + 24 * 1024) + warp * 2;
+    pr[0] = clock64() - prof_t0;
+    pr[1] = prof_wait;
+  }
+#endif
   // ---- every role is done (or gave up): report, release TMEM
   if (!ok) {
     *s_abort = 1;
@@ -1059,21 +1092,22 @@ bool step_ws_tiling(int S, int* Sp_out, int* R_out) {
   return true;
 }
 
-template <int KE>
+template <int KE, bool POSE>
 static int launch_ws(const StepArgs& a, int blocks, cudaStream_t st) {
   const size_t smem = step_ws_smem(KE);
   static_assert(sizeof(ws::TileHdr) == 80, "TileHdr layout");
-  cudaFuncSetAttribute(ws::step_ws_kernel<KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per-device attribute
+  cudaFuncSetAttribute(ws::step_ws_kernel<KE, POSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per-device attribute
   const ws::Plan sp = ws::make_plan(KE);
   if ((size_t)sp.img_bytes + 16 > kWPackBytes) { set_error("nof_step_fused(ws): operand image too large"); return NOF_E_INVALID; }
   ws::pack_ws_kernel<KE><<<(sp.img_bytes / 4 + 255) / 256, 256, 0, st>>>(a);
-  ws::step_ws_kernel<KE><<<blocks, ws::NT, smem, st>>>(a);
+  ws::step_ws_kernel<KE, POSE><<<blocks, ws::NT, smem, st>>>(a);
   return check_launch("step_ws_kernel");
 }
 
 int step_ws_dispatch(const StepArgs& a, int blocks, cudaStream_t st) {
-  if (a.KE == 32) return launch_ws<32>(a, blocks, st);
-  if (a.KE == 16) return launch_ws<16>(a, blocks, st);
+  const bool pose = a.p.need_pose_grad != 0;
+  if (a.KE == 32) return pose ? launch_ws<32, true>(a, blocks, st) : launch_ws<32, false>(a, blocks, st);
+  if (a.KE == 16) return pose ? launch_ws<16, true>(a, blocks, st) : launch_ws<16, false>(a, blocks, st);
   set_error("nof_step_fused(amp, ws): unsupported KE=%d", a.KE);
   return NOF_E_UNSUPPORTED;
 }

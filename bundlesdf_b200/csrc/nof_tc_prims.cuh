@@ -40,14 +40,19 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait. `abort_flag` (shared memory, may be null) lets one role's failure release every other role's waits.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag = nullptr) {
+// Bounded wait. `abort_flag` (shared memory, may be null) lets one role's failure release every other role's waits. The polling loop is
+// kept OUT of line: the warp-specialised kernel has dozens of wait sites and its roles compete for the instruction cache.
+static __device__ __noinline__ bool mbar_wait_slow(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
 #pragma unroll 1
   for (int it = 0; it < (1 << 22); ++it) {
     if (mbar_try(bar, parity)) return true;
     if (abort_flag && (it & 63) == 63 && *abort_flag) return false;
   }
   return false;
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag = nullptr) {
+  if (mbar_try(bar, parity)) return true;
+  return mbar_wait_slow(bar, parity, abort_flag);
 }
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
