@@ -6,7 +6,7 @@
 #include "nof_step_common.cuh"
 
 #ifndef NOF_AMP_IMPL_DEFAULT
-#define NOF_AMP_IMPL_DEFAULT 1
+#define NOF_AMP_IMPL_DEFAULT 3
 #endif
 
 namespace nof {
@@ -41,9 +41,12 @@ size_t step_ws_jscratch(int blocks);
 bool step_ws_tiling(int S, int* Sp_out, int* R_out);
 int step_ws_dispatch(const StepArgs& a, int blocks, cudaStream_t st);
 
-// The AMP step has three implementations: 2 = warp-specialised streaming pipeline on tcgen05 (nof_step_ws.cu; S <= 384; default),
-// 1 = the round-1 tcgen05 kernel (one 128-point tile per CTA iteration, S <= 128; NOF_AMP_IMPL=tc), 0 = mma.sync tiles (S <= 256;
-// NOF_AMP_IMPL=mma). 1 and 0 are kept as in-process cross-checks of 2.
+// The AMP step has three implementations, all behind nof_step_fused:
+//   1 "tc"  : tcgen05 tile kernel, every warp walks the phases of one 128-point tile together, 2 CTAs/SM (nof_step_tc.cu; S <= 128)
+//   0 "mma" : the same structure on mma.sync with 128/192/256-point tiles (nof_step_amp.cu; S <= 256)
+//   2 "ws"  : warp-specialised streaming pipeline on tcgen05, rays may span tiles (nof_step_ws.cu; S <= 384)
+//   3 "auto": the fastest measured on B200 for the given S (profiles/README.md): tc for S <= 128, mma for S <= 256, ws above (default).
+// Forcing 0/1/2 (nof_set_amp_impl, env NOF_AMP_IMPL=mma|tc|ws) keeps the three as in-process cross-checks of one another.
 static int g_amp_impl = -1;
 static int amp_impl() {
   if (g_amp_impl < 0) {
@@ -52,7 +55,13 @@ static int amp_impl() {
   }
   return g_amp_impl;
 }
-static bool amp_use_tcgen05() { return amp_impl() == 1; }
+// implementation actually used for S samples per ray under the current setting
+static int amp_impl_for(int S) {
+  const int m = amp_impl();
+  if (m == 2 || (m == 3 && S > 256)) return 2;
+  if (m == 0 || S > 128) return S <= 256 ? 0 : 2;          // tc carries S <= 128 only; mma S <= 256; beyond that only ws exists
+  return 1;
+}
 
 static void mlp_offsets(int E, int V, int32_t o[10], size_t* total) {
   const int sizes[10] = {64 * E, 64, 16 * 64, 16, 64 * (V + 15), 64, 64 * 64, 64, 3 * 64, 3};
@@ -96,7 +105,7 @@ using namespace nof;
 extern "C" int nof_version(void) { return NOF_VERSION; }
 extern "C" int nof_set_amp_impl(int impl) {
   const int old = nof::amp_impl();
-  nof::g_amp_impl = impl < 0 ? 0 : (impl > 2 ? 2 : impl);
+  nof::g_amp_impl = impl < 0 ? 0 : (impl > 3 ? 3 : impl);
   return old;
 }
 extern "C" const char* nof_last_error(void) { return g_err; }
@@ -186,7 +195,7 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
   a.wpack = p->workspace;                                   // [0, kWPackBytes): packed fp16 MLP operands (tcgen05 path)
   a.jws = static_cast<char*>(p->workspace) + kWPackBytes;   // then the per-CTA Jacobian scratch
   Tiling t;
-  if (p->amp && amp_impl() == 2) {
+  if (p->amp && amp_impl_for(p->S) == 2) {
     int Sp, R;
     NOF_REQUIRE(step_ws_tiling(p->S, &Sp, &R), "nof_step_fused(amp): S=%d > 384 samples per ray not supported (use amp: false)", p->S);
     a.R = R; a.Sp = Sp; a.n_groups = (p->N + R - 1) / R;
@@ -196,7 +205,7 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
   if (p->amp) {
     NOF_REQUIRE(amp_tiling(p, sms, &t), "nof_step_fused(amp): S=%d > 256 samples per ray not supported by the AMP tile (use amp: false)", p->S);
     a.R = t.R; a.Sp = t.Sp; a.n_groups = t.n_groups;
-    if (t.NW == 4 && amp_use_tcgen05()) {
+    if (t.NW == 4 && amp_impl_for(p->S) == 1) {
       NOF_REQUIRE(step_tc_smem(a.KE) <= (size_t)smem_max, "nof_step_fused(amp, tcgen05): needs %zu B shared memory, device allows %d",
                   step_tc_smem(a.KE), smem_max);
       return step_tc_dispatch(a, t.blocks, as_stream(stream));

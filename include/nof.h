@@ -210,9 +210,11 @@ size_t nof_step_workspace_bytes(const NofStep* p);
  * (nerf_runner.py:1083-1088, 1227-1304, 1132-1169, 679-758; grid.py:34-99; nerf_helpers.py:305-321,367-399).
  * Forward + backward are ONE kernel launch; no [P,*] intermediate is written to HBM. */
 int nof_step_fused(const NofStep* p, nof_stream_t stream);
-/* The AMP step with S <= 128 samples per ray has two interchangeable implementations of the MLP GEMM chain: tcgen05/TMEM
- * (impl 1, default) and warp-level mma.sync (impl 0; also what S in (128, 256] always uses). Same results within fp16
- * rounding; the switch exists so the two can be cross-checked (env NOF_AMP_IMPL=mma selects 0 at load). Returns the old value. */
+/* The AMP step has three interchangeable implementations of the same arithmetic: 1 = tcgen05/TMEM tile kernel (S <= 128), 0 = warp-level
+ * mma.sync tiles (S <= 256), 2 = warp-specialised streaming pipeline on tcgen05 whose rays may span tiles (S <= 384: the reference's
+ * config.yml 128+64 and run_custom.py 64+256 sample counts); 3 = automatic (default): the fastest measured for the given S. Same results
+ * within fp16 rounding; forcing one (env NOF_AMP_IMPL=mma|tc|ws at load) lets them be cross-checked. A forced implementation that cannot
+ * carry S falls through to the next one that can. Returns the old value. */
 int nof_set_amp_impl(int impl);
 
 typedef struct {

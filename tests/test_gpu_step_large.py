@@ -40,7 +40,9 @@ def _check(scene, res, ref, P, amp, scale):
     assert losses[5] == float(ref['valid_samples'].sum())
     assert _rel_max(res['grad_table'].cpu().numpy() / scale, P['embeddings'].grad.numpy()) < gtol
     for k, g in res['grad_mlp_named'].items():
-        assert _rel_max(g.cpu().numpy() / scale, P[k].grad.numpy()) < gtol, k
+        # bias gradients are plain sums over all N*S samples (262144 / 524288 terms here) of fp16-rounded dY with heavy cancellation:
+        # their AMP rounding noise relative to the small result is larger than for the weight matrices -> twice the tolerance
+        assert _rel_max(g.cpu().numpy() / scale, P[k].grad.numpy()) < (2 * gtol if (amp and k.endswith('bias')) else gtol), k
     assert _rel_max(res['grad_pose'].cpu().numpy(), P['pose_data'].grad.numpy()) < gtol * 2
     assert res['found_inf'].item() == 0
 
