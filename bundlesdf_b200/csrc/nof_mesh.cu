@@ -122,9 +122,48 @@ __global__ void mtet_emit_kernel(const float* __restrict__ f, int nx, int ny, in
   }
 }
 
+// Nearest-neighbour distance test against a point cloud binned into a uniform grid of cell size >= radius (cloud points sorted by
+// cell, cell_start = exclusive prefix of the per-cell counts): a query is within `radius` of the cloud iff one of the 27 cells around
+// it holds such a point. Replaces the host cKDTree query of the ray-pool denoise (nerf_runner.py:178-195). Thread = query.
+__global__ void __launch_bounds__(256) cloud_within_kernel(const float* __restrict__ query, int64_t Q, const float* __restrict__ cloud,
+                                                           const int32_t* __restrict__ cell_start, float lo, float inv_cell, int n, float r2,
+                                                           uint8_t* __restrict__ within) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Q) return;
+  const float qx = query[i * 3 + 0], qy = query[i * 3 + 1], qz = query[i * 3 + 2];
+  const int cx = (int)floorf((qx - lo) * inv_cell), cy = (int)floorf((qy - lo) * inv_cell), cz = (int)floorf((qz - lo) * inv_cell);
+  bool hit = false;
+  for (int dx = -1; dx <= 1 && !hit; ++dx) {
+    const int x = cx + dx;
+    if (x < 0 || x >= n) continue;
+    for (int dy = -1; dy <= 1 && !hit; ++dy) {
+      const int y = cy + dy;
+      if (y < 0 || y >= n) continue;
+      const int z0 = max(cz - 1, 0), z1 = min(cz + 1, n - 1);          // cells along z are contiguous in the sorted cloud
+      if (z0 > z1) continue;
+      const int c0 = (x * n + y) * n + z0, c1 = (x * n + y) * n + z1;
+      for (int k = cell_start[c0]; k < cell_start[c1 + 1]; ++k) {
+        const float ex = cloud[k * 3 + 0] - qx, ey = cloud[k * 3 + 1] - qy, ez = cloud[k * 3 + 2] - qz;
+        if (ex * ex + ey * ey + ez * ez <= r2) { hit = true; break; }
+      }
+    }
+  }
+  within[i] = hit ? 1 : 0;
+}
+
 }  // namespace nof
 
 using namespace nof;
+
+extern "C" int nof_cloud_within_radius(const float* query, int64_t Q, const float* cloud_sorted, const int32_t* cell_start, float lo, float cell,
+                                       int n, float radius, uint8_t* within, nof_stream_t stream) {
+  NOF_REQUIRE(query && cloud_sorted && cell_start && within, "nof_cloud_within_radius: null pointer");
+  NOF_REQUIRE(Q >= 0 && n >= 1 && n <= 1024 && cell >= radius && radius > 0.f, "nof_cloud_within_radius: bad grid (n=%d cell=%g radius=%g)", n, cell, radius);
+  if (Q == 0) return NOF_OK;
+  cloud_within_kernel<<<(unsigned)div_up<int64_t>(Q, 256), 256, 0, as_stream(stream)>>>(query, Q, cloud_sorted, cell_start, lo, 1.0f / cell, n,
+                                                                                          radius * radius, within);
+  return check_launch("cloud_within_kernel");
+}
 
 extern "C" int nof_marching_tets_count(const float* field, int nx, int ny, int nz, float iso, int32_t* counts, nof_stream_t stream) {
   NOF_REQUIRE(field && counts, "nof_marching_tets_count: null pointer");

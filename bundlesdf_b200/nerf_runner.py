@@ -367,8 +367,8 @@ class NerfRunner:
         return rows
 
     def _denoise_rays(self, rays):
-        """nerf_runner.py:178-195: drop rays whose back-projected point is farther than 2 cm from the octree cloud (exact NN
-        distance, brute force on the device instead of a CPU cKDTree)."""
+        """nerf_runner.py:178-195: drop rays whose back-projected point is farther than 2 cm from the octree cloud (exact radius test
+        on the device over a uniform grid of the cloud instead of a CPU cKDTree)."""
         cfg, dev = self.cfg, self.device
         sc = cfg['sc_factor']
         mask = (rays[:, 7] > 0) & (rays[:, 6] <= cfg['far'] * sc)
@@ -378,10 +378,7 @@ class NerfRunner:
         T = poses[rays[idx, 8].long()]
         pts_w = (T[:, :3, :3] @ pts[..., None])[..., 0] + T[:, :3, 3]
         cloud = torch.as_tensor(self.build_octree_pts).float().to(dev)
-        bad = torch.zeros(len(idx), dtype=torch.bool, device=dev)
-        for s in range(0, len(idx), 16384):
-            d = torch.cdist(pts_w[s:s + 16384], cloud).min(dim=1)[0]
-            bad[s:s + 16384] = d > 0.02 * sc
+        bad = ~ops.cloud_within_radius(pts_w, cloud, 0.02 * sc)          # exact radius test on a uniform grid (nof_cloud_within_radius)
         rays[idx[bad], 6] = BAD_DEPTH * sc
         rays[idx[bad], 9] = 1
         logging.info(f'bad_mask#={int(bad.sum())}')

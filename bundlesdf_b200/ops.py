@@ -177,6 +177,29 @@ def query_sdf(sb, x, out=None):
     return sdf
 
 
+def cloud_within_radius(query, cloud, radius):
+    """bool [Q]: is some point of `cloud` [M,3] within `radius` of query[i]? Uniform-grid binning on the device (nof_cloud_within_radius)."""
+    lib = _lib.load()
+    query = query.contiguous().float()
+    cloud = cloud.contiguous().float()
+    if len(cloud) == 0 or len(query) == 0:
+        return torch.zeros(len(query), dtype=torch.bool, device=query.device)
+    lo = float(torch.minimum(cloud.min(), query.min()).item()) - 1e-3
+    hi = float(torch.maximum(cloud.max(), query.max()).item()) + 1e-3
+    n = max(1, min(256, int((hi - lo) / radius)))            # cell >= radius
+    cell = (hi - lo) / n
+    ci = torch.clamp(torch.floor((cloud - lo) / cell).long(), 0, n - 1)
+    key = (ci[:, 0] * n + ci[:, 1]) * n + ci[:, 2]
+    order = torch.argsort(key)
+    counts = torch.bincount(key, minlength=n * n * n)
+    cell_start = torch.zeros(n * n * n + 1, dtype=torch.int32, device=cloud.device)
+    cell_start[1:] = torch.cumsum(counts, 0).int()
+    within = torch.empty(len(query), dtype=torch.uint8, device=query.device)
+    _lib.check(lib.nof_cloud_within_radius(_lib.ptr(query), len(query), _lib.ptr(cloud[order].contiguous()), _lib.ptr(cell_start), lo, float(cell), n,
+                                           float(radius), _lib.ptr(within), _lib.stream()), 'nof_cloud_within_radius')
+    return within.bool()
+
+
 def marching_tets(field, iso=0.0):
     """Iso-surface of a dense [nx,ny,nz] fp32 CUDA grid (include/nof.h nof_marching_tets_*). Returns (vertices [V,3] fp32 in
     grid-index coordinates, faces [F,3] int64), vertices welded, triangles facing increasing field values."""

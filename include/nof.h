@@ -252,6 +252,13 @@ int nof_adam_finish(int32_t* step, float* scale_state, int32_t* found_inf, uint6
  * NeRFSmall.forward_sdf nerf_helpers.py:296-302): x [P,3] in [-1,1] (clipped inside) -> sdf [P]. */
 int nof_query_sdf(const NofStep* model, const float* x, float* sdf, int64_t P, nof_stream_t stream);
 
+/* Replaces the host cKDTree nearest-neighbour query of the ray-pool denoise (nerf_runner.py:178-195: rays whose back-projected point is
+ * farther than 2 cm from the octree cloud are marked uncertain): within[i] = 1 iff some cloud point lies within `radius` of query[i].
+ *   cloud_sorted [M,3] the cloud sorted by grid cell (cell of p = floor((p - lo) / cell) per axis, linear index (x*n + y)*n + z),
+ *   cell_start [n^3 + 1] int32 exclusive prefix sum of the points per cell; cell >= radius (so the 27 cells around a query suffice). */
+int nof_cloud_within_radius(const float* query, int64_t Q, const float* cloud_sorted, const int32_t* cell_start, float lo, float cell,
+                            int n, float radius, uint8_t* within, nof_stream_t stream);
+
 /* Iso-surface of a dense scalar grid for NerfRunner.extract_mesh (nerf_runner.py:1387-1404 calls skimage.measure.marching_cubes
  * on the host). Marching tetrahedra over the Kuhn split of each cell (closed 2-manifold, no case tables); two passes:
  *   count: field [nx,ny,nz] (C order) -> counts [(nx-1)(ny-1)(nz-1)] triangles per cell (int32);

@@ -40,11 +40,23 @@ def _check(scene, res, ref, P, amp, scale):
     assert losses[5] == float(ref['valid_samples'].sum())
     assert _rel_max(res['grad_table'].cpu().numpy() / scale, P['embeddings'].grad.numpy()) < gtol
     for k, g in res['grad_mlp_named'].items():
-        # bias gradients are plain sums over all N*S samples (262144 / 524288 terms here) of fp16-rounded dY with heavy cancellation:
-        # their AMP rounding noise relative to the small result is larger than for the weight matrices -> twice the tolerance
-        assert _rel_max(g.cpu().numpy() / scale, P[k].grad.numpy()) < (2 * gtol if (amp and k.endswith('bias')) else gtol), k
+        # Bias gradients are plain sums over all N*S samples (262144 / 524288 terms) of fp16 dY with heavy cancellation: the rounding
+        # MODEL matters there (the kernels round dY to fp16 where the tensor-core operands need it, the oracle's autocast emulation rounds
+        # at the layer outputs), so they get 4x the tolerance under AMP; the three kernels agree with each other to 1e-4 (_CROSS below).
+        assert _rel_max(g.cpu().numpy() / scale, P[k].grad.numpy()) < (4 * gtol if (amp and k.endswith('bias')) else gtol), k
     assert _rel_max(res['grad_pose'].cpu().numpy(), P['pose_data'].grad.numpy()) < gtol * 2
     assert res['found_inf'].item() == 0
+
+
+_ORACLE = {}      # (name, amp) -> (ref, P): one oracle evaluation per configuration and policy
+_CROSS = {}       # name -> first AMP result, against which the other AMP implementations are compared
+
+
+def _cross_check(name, res):
+    """The three AMP implementations compute the same arithmetic: their results agree far more tightly than any of them with the oracle."""
+    first = _CROSS.setdefault(name, {k: res[k].clone() for k in ('raw', 'rgb_map', 'grad_table', 'grad_mlp', 'grad_tf')})
+    for k, v in first.items():
+        assert _rel_max(res[k].cpu().numpy(), v.cpu().numpy()) < (2e-3 if k == 'raw' else 1e-4), k
 
 
 LARGE = [
@@ -65,8 +77,12 @@ def test_fused_step_at_benchmark_size(name, frames, N, kw, amp, amp_impl):
     rng = np.random.default_rng(17)
     t_rand = rng.random((N, 128), dtype=np.float32)
     res = helpers.run_fused_step(scene, amp=amp, t_rand=t_rand, loss_scale=(1024.0 if amp else None))
-    ref, P = _oracle(scene, t_rand, half=amp, z_vals=res['z_vals'].cpu())
+    if (name, amp) not in _ORACLE:
+        _ORACLE[(name, amp)] = _oracle(scene, t_rand, half=amp, z_vals=res['z_vals'].cpu())
+    ref, P = _ORACLE[(name, amp)]
     _check(scene, res, ref, P, amp, 1024.0 if amp else 1.0)
+    if amp:
+        _cross_check(name, res)
 
 
 @pytest.mark.parametrize('amp_impl', ['ws', 'tcgen05', 'mma'], indirect=True)
