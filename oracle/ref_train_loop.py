@@ -70,7 +70,7 @@ def reference_modules():
     return _MODS
 
 
-def build_reference_runner(ours):
+def build_reference_runner(ours, init_scale=65536.0):
     """A reference NerfRunner that shares `ours`' data (cfg, ray pool, occupancy, initial poses) and owns its own models/optimizer,
     built by the reference's create_nerf / create_optimizer. __init__ is bypassed (it needs open3d / kaolin / cv2 windows)."""
     nh, nr, U = reference_modules()
@@ -89,7 +89,7 @@ def build_reference_runner(ours):
     ref.ray_frame_id_slice, ref.ray_type_slice, ref.ray_near_slice, ref.ray_far_slice = 8, 9, 10, 11
     ref.create_nerf()
     ref.create_optimizer()
-    ref.amp_scaler = torch.cuda.amp.GradScaler(enabled=bool(ref.cfg['amp']))
+    ref.amp_scaler = torch.cuda.amp.GradScaler(init_scale=init_scale, enabled=bool(ref.cfg['amp']))   # nerf_runner.py:159 (default 65536)
     ref.data_loader = nr.DataLoader(rays=ref.rays, batch_size=ref.cfg['N_rand'])
     return ref
 
@@ -117,10 +117,13 @@ def time_reference(c, name, steps=10, warmup=3):
                     "sm_100a (oracle/_ref), PyTorch eager, on this B200; kaolin's ray trace replaced by the product's DDA (third-party, absent)"}
 
 
-def golden_step(ours, batch, seed=0):
+def golden_step(ours, batch, seed=0, init_scale=1024.0):
     """One verbatim reference train_loop on `batch` with the reference's own freshly initialised models; returns a dict of numpy arrays
-    with everything the step-level parity test needs. The gradients are read between backward() and the optimizer step."""
-    ref = build_reference_runner(ours)
+    with everything the step-level parity test needs. The gradients are read between backward() and the optimizer step.
+    init_scale: GradScaler scale of the AMP run. With the reference's default 65536 the very first step overflows in fp16 (observed on
+    the B200: sigma_net.2.bias.grad[0] = inf — the reference accumulates bias gradients in fp16 — and GradScaler skips the step); the
+    golden uses 1024 so that every gradient of the step is finite and comparable."""
+    ref = build_reference_runner(ours, init_scale=init_scale)
     torch.manual_seed(seed)
     cap = {}
     N = batch.shape[0]

@@ -64,7 +64,7 @@ CASES = [
     (4, 128, 14, 24, 20, 33, 1, dict(invalid_frac=0.2)),               # S=44: padded lanes inside the tile, odd ray count, ff=1
     (16, 256, 12, 64, 256, 11, 0, dict(invalid_frac=0.1)),             # run_custom.py:122-123 split 64+256 = 320: rays span three tiles
     (16, 256, 12, 128, 128, 9, 1, {}),                                 # S=256: one ray = two tiles
-    (6, 128, 14, 100, 60, 13, 0, {}),                                  # S=160 (padded to 192 lanes per ray), L=6 (operand width padded to 16)
+    (6, 128, 14, 100, 60, 24, 0, {}),                                  # S=160 (padded to 192 lanes per ray), L=6 (operand width padded to 16)
 ]
 
 
