@@ -36,7 +36,7 @@ class NofStep(C.Structure):
                 ('fs_rgb_weight', _f32), ('first_frame_weight', _f32),
                 ('loss_scale', _vp), ('need_pose_grad', _i32),
                 ('grad_table', _vp), ('grad_mlp', _vp), ('grad_tf', _vp), ('grad_feat', _vp), ('losses', _vp), ('found_inf', _vp),
-                ('rgb_map', _vp), ('raw', _vp), ('valid_samples', _vp), ('weights', _vp), ('workspace', _vp)]
+                ('rgb_map', _vp), ('raw', _vp), ('valid_samples', _vp), ('weights', _vp), ('workspace', _vp), ('eikonal_weight', _f32)]
 
 
 class NofAdamSeg(C.Structure):

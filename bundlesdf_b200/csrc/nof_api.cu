@@ -30,7 +30,7 @@ int check_launch(const char* what) {
   return NOF_OK;
 }
 
-size_t step_amp_smem(int T, int KE);
+size_t step_amp_smem(int T, int KE, bool eik);
 size_t step_f32_smem(int E, int V, int grp_pts);
 int step_amp_dispatch(const StepArgs& a, int NW, int blocks, cudaStream_t st);
 int step_f32_dispatch(const StepArgs& a, int blocks, cudaStream_t st);
@@ -69,6 +69,9 @@ static void mlp_offsets(int E, int V, int32_t o[10], size_t* total) {
   for (int i = 0; i < 10; ++i) { o[i] = acc; acc += sizes[i]; }
   if (total) *total = (size_t)acc;
 }
+
+template <bool HALF, bool COUNT>
+__global__ void query_sdf_kernel(const StepArgs a, const float* __restrict__ xin, float* __restrict__ sdf, int64_t P, int* __restrict__ count);
 
 struct Tiling { int NW, Sp, R, n_groups, blocks; };
 
@@ -195,7 +198,20 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
   a.wpack = p->workspace;                                   // [0, kWPackBytes): packed fp16 MLP operands (tcgen05 path)
   a.jws = static_cast<char*>(p->workspace) + kWPackBytes;   // then the per-CTA Jacobian scratch
   Tiling t;
-  if (p->amp && amp_impl_for(p->S) == 2) {
+  const bool eik = p->eikonal_weight > 0.f;
+  NOF_REQUIRE(!eik || (p->amp && p->S <= 256), "nof_step_fused: eikonal_weight > 0 is built for amp: true and S <= 256 (S=%d amp=%d)", p->S, p->amp);
+  if (eik) {
+    // the term is a mean over the selected samples of the WHOLE batch: count them first (SDF-only forward of all N*S samples)
+    int* cnt = reinterpret_cast<int*>(static_cast<char*>(a.wpack) + kWPackBytes - 32);
+    cudaMemsetAsync(cnt, 0, sizeof(int), as_stream(stream));
+    const int64_t P = (int64_t)p->N * p->S;
+    const size_t smem_q = (size_t)(64 * a.E + 128) * 4;
+    const int qblocks = (int)std::min<int64_t>((P + 255) / 256, (int64_t)sms * 8);
+    query_sdf_kernel<true, true><<<qblocks, 256, smem_q, as_stream(stream)>>>(a, nullptr, nullptr, P, cnt);
+    rc = check_launch("eik_count (query_sdf_kernel)");
+    if (rc) return rc;
+  }
+  if (p->amp && !eik && amp_impl_for(p->S) == 2) {
     int Sp, R;
     NOF_REQUIRE(step_ws_tiling(p->S, &Sp, &R), "nof_step_fused(amp): S=%d > 384 samples per ray not supported (use amp: false)", p->S);
     a.R = R; a.Sp = Sp; a.n_groups = (p->N + R - 1) / R;
@@ -205,13 +221,13 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
   if (p->amp) {
     NOF_REQUIRE(amp_tiling(p, sms, &t), "nof_step_fused(amp): S=%d > 256 samples per ray not supported by the AMP tile (use amp: false)", p->S);
     a.R = t.R; a.Sp = t.Sp; a.n_groups = t.n_groups;
-    if (t.NW == 4 && amp_impl_for(p->S) == 1) {
+    if (t.NW == 4 && !eik && amp_impl_for(p->S) == 1) {
       NOF_REQUIRE(step_tc_smem(a.KE) <= (size_t)smem_max, "nof_step_fused(amp, tcgen05): needs %zu B shared memory, device allows %d",
                   step_tc_smem(a.KE), smem_max);
       return step_tc_dispatch(a, t.blocks, as_stream(stream));
     }
-    NOF_REQUIRE(step_amp_smem(t.NW * 32, a.KE) <= (size_t)smem_max, "nof_step_fused(amp): needs %zu B shared memory, device allows %d",
-                step_amp_smem(t.NW * 32, a.KE), smem_max);
+    NOF_REQUIRE(step_amp_smem(t.NW * 32, a.KE, eik) <= (size_t)smem_max, "nof_step_fused(amp): needs %zu B shared memory, device allows %d",
+                step_amp_smem(t.NW * 32, a.KE, eik), smem_max);
     zero_step_outputs(p, as_stream(stream));
     return step_amp_dispatch(a, t.NW, t.blocks, as_stream(stream));
   }
@@ -227,8 +243,10 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
 // SDF-only query (mesh extraction): encode + sigma_net, thread = point, weights broadcast from shared memory.
 // ------------------------------------------------------------------------------------------------
 namespace nof {
-template <bool HALF>
-__global__ void __launch_bounds__(256) query_sdf_kernel(const StepArgs a, const float* __restrict__ xin, float* __restrict__ sdf, int64_t P) {
+// COUNT: instead of writing the sdf of given points, visit the N*S samples of the batch (rays, tf, z_vals) and count those the eikonal
+// term averages over: sdf < 1, out-of-bounds samples included with sdf = 0 (oracle.eikonal_loss / nerf_runner.py:737 `normals[sdf<1]`).
+template <bool HALF, bool COUNT>
+__global__ void __launch_bounds__(256) query_sdf_kernel(const StepArgs a, const float* __restrict__ xin, float* __restrict__ sdf, int64_t P, int* __restrict__ count) {
   extern __shared__ __align__(16) float sq[];
   __shared__ LevelS lv;
   const int E = a.E;
@@ -246,10 +264,28 @@ __global__ void __launch_bounds__(256) query_sdf_kernel(const StepArgs a, const 
   if (HALF) b2 = __half2float(__float2half_rn(b2));
   init_levels(lv, a);
   __syncthreads();
+  int n_sel = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
     float u[3];
+    if (COUNT) {
+      const int ray = (int)(i / a.p.S);
+      const float* row = a.p.rays + (size_t)ray * a.p.ray_dim;
+      const int frame = min(max((int)row[8], 0), a.p.F - 1);
+      const float* T = a.p.tf + (size_t)frame * 12;
+      const float z = a.p.z_vals[i];
+      const float pc[3] = {row[0] * z, row[1] * z, row[2] * z};
+      bool valid = true;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) u[d] = (fminf(fmaxf(xin[i * 3 + d], -1.f), 1.f) + 1.f) * 0.5f;   // nerf_runner.py:1314, grid.py:160
+      for (int d = 0; d < 3; ++d) {                             // same arithmetic as world_point of the step kernels
+        const float x = fmaf(T[d * 4 + 2], pc[2], fmaf(T[d * 4 + 1], pc[1], T[d * 4 + 0] * pc[0])) + T[d * 4 + 3];
+        valid = valid && fabsf(x) <= 1.f;
+        u[d] = (x + 1.0f) * 0.5f;
+      }
+      if (!valid) { ++n_sel; continue; }
+    } else {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) u[d] = (fminf(fmaxf(xin[i * 3 + d], -1.f), 1.f) + 1.f) * 0.5f;   // nerf_runner.py:1314, grid.py:160
+    }
     float enc[32];
 #pragma unroll
     for (int l = 0; l < MAX_L; ++l) {
@@ -268,7 +304,13 @@ __global__ void __launch_bounds__(256) query_sdf_kernel(const StepArgs a, const 
       if (HALF) acc = __half2float(__float2half_rn(acc));
       out = fmaf(acc, sW2[o], out);
     }
-    sdf[i] = HALF ? __half2float(__float2half_rn(out)) : out;
+    const float res = HALF ? __half2float(__float2half_rn(out)) : out;
+    if (COUNT) n_sel += res < 1.f ? 1 : 0;
+    else sdf[i] = res;
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) n_sel += __shfl_xor_sync(0xffffffffu, n_sel, o);
+    if ((threadIdx.x & 31) == 0 && n_sel) atomicAdd(count, n_sel);
   }
 }
 }  // namespace nof
@@ -290,7 +332,7 @@ extern "C" int nof_query_sdf(const NofStep* model, const float* x, float* sdf, i
   nof_device_info(&sms, nullptr);
   const size_t smem = (size_t)(64 * a.E + 128) * 4;
   const int blocks = (int)std::min<int64_t>((P + 255) / 256, (int64_t)sms * 8);
-  if (model->amp) query_sdf_kernel<true><<<blocks, 256, smem, as_stream(stream)>>>(a, x, sdf, P);
-  else query_sdf_kernel<false><<<blocks, 256, smem, as_stream(stream)>>>(a, x, sdf, P);
+  if (model->amp) query_sdf_kernel<true, false><<<blocks, 256, smem, as_stream(stream)>>>(a, x, sdf, P, nullptr);
+  else query_sdf_kernel<false, false><<<blocks, 256, smem, as_stream(stream)>>>(a, x, sdf, P, nullptr);
   return check_launch("query_sdf_kernel");
 }

@@ -76,11 +76,11 @@ constexpr int LD32 = 40;   // stride of 32-wide
 constexpr int LD16 = 24;   // stride of 16-wide
 
 struct SmemPlan {
-  int w1, w2, w3, w4, w5, bias, x0, x1, xc, x3, x4, d_o, out, rays, lv, bar, total;   // byte offsets
+  int w1, w2, w3, w4, w5, bias, x0, x1, xc, x3, x4, d_o, out, rays, lv, bar, qh, nbuf, total;   // byte offsets
   int ldx0;                // stride (halfs) of X0 / W1 (KE + 8)
 };
 
-__host__ __device__ inline SmemPlan make_plan(int PT, int KE) {
+__host__ __device__ inline SmemPlan make_plan(int PT, int KE, bool eik = false) {
   SmemPlan s;
   s.ldx0 = KE + 8;
   int o = 0;
@@ -101,6 +101,8 @@ __host__ __device__ inline SmemPlan make_plan(int PT, int KE) {
   s.rays = take(MAX_R * (int)sizeof(RayS));
   s.lv = take((int)sizeof(LevelS));
   s.bar = take(64);
+  s.qh = take(eik ? PT * s.ldx0 * 2 : 0);      // eikonal: q = d sdf / d enc of every point (fp16), kept until the scatter
+  s.nbuf = take(eik ? 2 * PT * 3 * 4 : 0);     // eikonal: the two half-sums of the normal
   s.total = o;
   return s;
 }
@@ -260,14 +262,14 @@ __device__ __forceinline__ bool store_masked64(__half* X, int row0, const float 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int PT, int KE_>
-__global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(const StepArgs a) {
+template <int PT, int KE_, bool EIK>
+__global__ void __launch_bounds__(2 * PT, (PT <= 128 && !EIK) ? 2 : 1) step_amp_kernel(const StepArgs a) {
   constexpr int NT = 2 * PT;                 // threads
   constexpr int NWARP = NT / 32;
   constexpr int KE = KE_;
   constexpr int LDX0 = KE + 8;
   extern __shared__ __align__(128) unsigned char smem[];
-  const SmemPlan sp = make_plan(PT, KE);
+  const SmemPlan sp = make_plan(PT, KE, EIK);
   __half* sW1 = reinterpret_cast<__half*>(smem + sp.w1);
   __half* sW2 = reinterpret_cast<__half*>(smem + sp.w2);
   __half* sW3 = reinterpret_cast<__half*>(smem + sp.w3);
@@ -336,6 +338,14 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
   float loss_acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   float n_valid_s = 0.f, n_valid_r = 0.f;
   bool overflow = false;
+  // eikonal term: its weight over the number of selected samples (counted by eik_count_kernel before this launch),
+  // times the loss scale; accumulators of d L_eik / d W2[0,:] (lanes with g8 == 0 own columns nt*8 + 2*t4, +1)
+  float eik_loss = 0.f, w2e[8][2];
+  __half* Qh = reinterpret_cast<__half*>(smem + sp.qh);
+  float* nbuf = reinterpret_cast<float*>(smem + sp.nbuf);
+  const float eik_c = EIK ? a.p.eikonal_weight / fmaxf((float)*reinterpret_cast<const int*>(static_cast<const char*>(a.wpack) + kWPackBytes - 32), 1.f) : 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) w2e[nt][0] = w2e[nt][1] = 0.f;
 
   const int Sp = a.Sp, R = a.R, S = a.p.S;
   // point owned by this thread in the per-point phases: both halves of the CTA see the same points
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
 #pragma unroll kGatherUnroll
         for (int l = l_beg; l < l_end; ++l) {
           float enc[2], J[3][2];
-          if (a.p.need_pose_grad) {
+          if (EIK || a.p.need_pose_grad) {
             gather_level<true, true>(a.p.table_f16, lv, l, u, enc, J);
 #pragma unroll
             for (int d = 0; d < 3; ++d) Jslot[(size_t)(l * 3 + d) * PT + pt] = __floats2half2_rn(J[d][0], J[d][1]);
@@ -398,6 +408,115 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
       }
     }
     __syncthreads();                                        // (A) rows are produced by two different warps
+    // ============ eikonal term (the INTENDED maths of nerf_runner.py:734-738, 1297-1302, 1342-1345, defined by oracle.eikonal_loss):
+    // n = d sdf / d x = 1/2 J^T q with q = W1^T (relu'(h1) * W2[0,:]) the gradient of the sdf w.r.t. the encoding; L = w/C sum (|n| - 1)^2
+    // over the samples with sdf < 1 (C of them, counted beforehand). With g = dL/dn: dL/dq = a = 1/2 J g, dL/dW2[0,:] = relu'(h1) * (W1 a),
+    // dL/dW1 = (relu'(h1) * W2[0,:]) (x) a, and the table receives 1/2 q_c g_d scale_l dw_k/df_d per corner (scatter). x is detached.
+    float eg[3] = {0.f, 0.f, 0.f};                          // g of this thread's point (both threads of a point hold it)
+    auto eikonal_block = [&]() {
+      __half* XR = X3;                                      // relu'(h1) * W2[0,:]  (X3 / X4 are free until layers 3 / 4 of the forward)
+      __half* XA = X4;                                      // a, row stride LDX0
+      {                                                     // e1: own 16 rows, lane = (row, half of the 64 columns)
+        const int r = row0 + (lane >> 1), c0 = (lane & 1) * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const __half2 m = *reinterpret_cast<const __half2*>(X1 + (size_t)r * LD64 + c0 + j);
+          const __half2 w = *reinterpret_cast<const __half2*>(sW2 + c0 + j);
+          const uint32_t keep = __hgt2_mask(m, __float2half2_rn(0.f));
+          *reinterpret_cast<uint32_t*>(XR + (size_t)r * LD64 + c0 + j) = *reinterpret_cast<const uint32_t*>(&w) & keep;
+        }
+      }
+      __syncwarp();
+      {                                                     // e2: q = r W1 on the tensor cores, stored as fp16
+        constexpr int NT1 = KE / 8;
+        float acc[NT1][4];
+        zero_acc<NT1>(acc);
+        warp_dgrad<64, KE>(XR + (size_t)row0 * LD64, LD64, sW1, LDX0, acc, lane);
+#pragma unroll
+        for (int nt = 0; nt < NT1; ++nt) {
+          __half* y = Qh + (size_t)(row0 + g8) * LDX0 + nt * 8 + 2 * t4;
+          *reinterpret_cast<uint32_t*>(y) = pack_h2(acc[nt][0], acc[nt][1]);
+          *reinterpret_cast<uint32_t*>(y + 8 * LDX0) = pack_h2(acc[nt][2], acc[nt][3]);
+        }
+      }
+      __syncthreads();                                      // (E1) q of every point visible to the point's two threads
+      {                                                     // e3: this thread's levels of n = 1/2 J^T q
+        float nh[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          for (int l = l_beg; l < l_end; ++l) {
+            const float2 q = __half22float2(*reinterpret_cast<const __half2*>(Qh + (size_t)pt * LDX0 + 2 * l));
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const float2 jj = __half22float2(Jslot[(size_t)(l * 3 + d) * PT + pt]);
+              nh[d] = fmaf(q.x, jj.x, fmaf(q.y, jj.y, nh[d]));
+            }
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) nbuf[(size_t)(half * PT + pt) * 3 + d] = 0.5f * nh[d];
+      }
+      __syncthreads();                                      // (E2)
+      {                                                     // e4: |n|, selection (sdf < 1; out-of-bounds samples have sdf = 0, n = 0), g = dL/dn
+        float n[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) n[d] = nbuf[(size_t)pt * 3 + d] + nbuf[(size_t)(PT + pt) * 3 + d];
+        const float sdf = sOut[pt * 4 + 3];
+        if (active) {
+          if (!valid) {
+            if (owner) eik_loss += eik_c;                   // (0 - 1)^2
+          } else if (sdf < 1.f) {
+            const float nn = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            if (owner) eik_loss += eik_c * (nn - 1.f) * (nn - 1.f);
+            const float coef = nn > 0.f ? eik_c * 2.f * (nn - 1.f) / nn * scale_ls : 0.f;      // the norm's subgradient at 0 is 0 (torch)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) eg[d] = coef * n[d];
+          }
+        }
+        // e5: a = 1/2 J g for this thread's levels -> XA (fp16 operand of the next two GEMMs)
+        __half* xa = XA + (size_t)pt * LDX0;
+        for (int l = l_beg; l < l_end; ++l) {
+          float a0 = 0.f, a1 = 0.f;
+          if (valid && (eg[0] != 0.f || eg[1] != 0.f || eg[2] != 0.f)) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const float2 jj = __half22float2(Jslot[(size_t)(l * 3 + d) * PT + pt]);
+              a0 = fmaf(jj.x, eg[d], a0);
+              a1 = fmaf(jj.y, eg[d], a1);
+            }
+            a0 *= 0.5f; a1 *= 0.5f;
+            overflow |= !(fabsf(a0) <= 65504.f) || !(fabsf(a1) <= 65504.f);
+          }
+          *reinterpret_cast<uint32_t*>(xa + 2 * l) = pack_h2(a0, a1);
+        }
+        if (owner) for (int j = E; j < KE; ++j) xa[j] = __float2half_rn(0.f);
+      }
+      __syncthreads();                                      // (E3) a of every row complete
+      {                                                     // e6: t = a W1^T on own rows; dW2[0,:] += column sums of relu'(h1) * t
+        float acc[8][4];
+        zero_acc<8>(acc);
+        warp_fwd<KE, 64>(XA + (size_t)row0 * LDX0, LDX0, sW1, LDX0, acc, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const __half2 m0 = *reinterpret_cast<const __half2*>(X1 + (size_t)(row0 + g8) * LD64 + nt * 8 + 2 * t4);
+          const __half2 m1 = *reinterpret_cast<const __half2*>(X1 + (size_t)(row0 + g8 + 8) * LD64 + nt * 8 + 2 * t4);
+          float s0 = (__low2float(m0) > 0.f ? acc[nt][0] : 0.f) + (__low2float(m1) > 0.f ? acc[nt][2] : 0.f);
+          float s1 = (__high2float(m0) > 0.f ? acc[nt][1] : 0.f) + (__high2float(m1) > 0.f ? acc[nt][3] : 0.f);
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          }
+          w2e[nt][0] += s0;
+          w2e[nt][1] += s1;
+        }
+      }
+      // e7: dW1 += r^T a over all rows of the tile (same split as the layer-1 weight gradient, no bias part)
+      if (warp < S1::ITEMS) {
+        float nob[2] = {0.f, 0.f};
+        wgrad_item<S1::CNT>(XR, LD64, XA, LDX0, PT, warp / S1::GROUPS, (warp % S1::GROUPS) * S1::CNT, wg1, nob, false, lane);
+      }
+      __syncthreads();                                      // (E4) X3 / X4 are free again for layers 3 / 4
+    };
     // ============ 3. MLP forward on the warp's own 16 rows
     {
       float acc[8][4];
@@ -424,6 +543,7 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
           }
         }
       __syncwarp();
+      if constexpr (EIK) eikonal_block();
       // ---- L3: (V+15 padded 32) -> 64, ReLU
       init_bias<8>(acc, sB + 80, t4);
       warp_fwd<KC, 64>(XC + (size_t)row0 * LD32, LD32, sW3, LD32, acc, lane);
@@ -596,6 +716,10 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
 #pragma unroll 2
         for (int l = l_beg; l < l_end; ++l) {
           const float2 g = *reinterpret_cast<const float2*>(dE + 2 * l);
+          if constexpr (EIK) {
+            const float2 q = __half22float2(*reinterpret_cast<const __half2*>(Qh + (size_t)pt * LDX0 + 2 * l));
+            if (g.x != 0.f || g.y != 0.f || eg[0] != 0.f || eg[1] != 0.f || eg[2] != 0.f) scatter_level_eik(a.p.grad_table, lv, l, u, g.x, g.y, q.x, q.y, eg);
+          } else
           if (g.x != 0.f || g.y != 0.f) scatter_level(a.p.grad_table, lv, l, u, g.x, g.y);
           if (a.p.need_pose_grad) {
 #pragma unroll
@@ -669,10 +793,19 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
       flush_item<S5::CNT>(G, a.po[8], a.po[9], 64, 3, 0, (warp % S5::GROUPS) * S5::CNT, wg5, wb5, (warp % S5::GROUPS) == 0, g8, t4);
   }
   {
-    loss_acc[0] = loss_acc[1] + loss_acc[2] + loss_acc[3] + loss_acc[4];
-    float vals[7] = {loss_acc[0], loss_acc[1], loss_acc[2], loss_acc[3], loss_acc[4], n_valid_s, n_valid_r};
+    if constexpr (EIK) {
+      if (g8 == 0) {
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
+        for (int nt = 0; nt < 8; ++nt) {
+          if (w2e[nt][0] != 0.f) red_add(a.p.grad_mlp + a.po[2] + nt * 8 + 2 * t4, w2e[nt][0]);
+          if (w2e[nt][1] != 0.f) red_add(a.p.grad_mlp + a.po[2] + nt * 8 + 2 * t4 + 1, w2e[nt][1]);
+        }
+      }
+    }
+    loss_acc[0] = loss_acc[1] + loss_acc[2] + loss_acc[3] + loss_acc[4] + eik_loss;
+    float vals[8] = {loss_acc[0], loss_acc[1], loss_acc[2], loss_acc[3], loss_acc[4], n_valid_s, n_valid_r, eik_loss};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
       const float v = warp_sum(vals[i]);
       if (lane == 0 && v != 0.f) red_add(a.p.losses + i, v);
     }
@@ -682,23 +815,24 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128) ? 2 : 1) step_amp_kernel(c
 }
 
 // ------------------------------------------------------------------------------------------------
-size_t step_amp_smem(int PT, int KE) { return (size_t)make_plan(PT, KE).total; }
+size_t step_amp_smem(int PT, int KE, bool eik) { return (size_t)make_plan(PT, KE, eik).total; }
 
-template <int PT, int KE>
+template <int PT, int KE, bool EIK>
 static int launch_amp(const StepArgs& a, int blocks, cudaStream_t st) {
-  const size_t smem = step_amp_smem(PT, KE);
+  const size_t smem = step_amp_smem(PT, KE, EIK);
   // function attributes are per device: set on every launch (a cheap host-side call) rather than once per process
-  cudaFuncSetAttribute(step_amp_kernel<PT, KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  step_amp_kernel<PT, KE><<<blocks, 2 * PT, smem, st>>>(a);
+  cudaFuncSetAttribute(step_amp_kernel<PT, KE, EIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  step_amp_kernel<PT, KE, EIK><<<blocks, 2 * PT, smem, st>>>(a);
   return check_launch("step_amp_kernel");
 }
 
 // NW = points per tile / 32 (4, 6 or 8)
 int step_amp_dispatch(const StepArgs& a, int NW, int blocks, cudaStream_t st) {
+  const bool eik = a.p.eikonal_weight > 0.f;
 #define NOF_AMP_CASE(nw)                                                          \
   case nw:                                                                        \
-    if (a.KE == 32) return launch_amp<nw * 32, 32>(a, blocks, st);                \
-    if (a.KE == 16) return launch_amp<nw * 32, 16>(a, blocks, st);                \
+    if (a.KE == 32) return eik ? launch_amp<nw * 32, 32, true>(a, blocks, st) : launch_amp<nw * 32, 32, false>(a, blocks, st);   \
+    if (a.KE == 16) return eik ? launch_amp<nw * 32, 16, true>(a, blocks, st) : launch_amp<nw * 32, 16, false>(a, blocks, st);   \
     break;
   switch (NW) {
     NOF_AMP_CASE(4)

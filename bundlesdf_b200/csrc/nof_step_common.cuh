@@ -286,6 +286,37 @@ __device__ __forceinline__ void scatter_level(float* grad_table, const LevelS& l
   }
 }
 
+// scatter_level plus the eikonal term's table gradient: corner k additionally receives 1/2 scale (g . dw_k/df) q_c, with dw_k/df_d the
+// derivative of the trilinear weight (w_k = prod_d (c_d ? f_d : 1 - f_d)), q = d sdf / d enc of this level, g = dL/dn.
+__device__ __forceinline__ void scatter_level_eik(float* grad_table, const LevelS& lv, int l, const float u[3], float g0, float g1, float q0, float q1,
+                                                  const float eg[3]) {
+  const float scale = lv.scale[l];
+  const uint32_t off = lv.off[l];
+  float fr[3];
+  uint32_t pg[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float p = fmaf(u[d], scale, 0.5f);
+    const float fl = floorf(p);
+    pg[d] = (uint32_t)fl;
+    fr[d] = p - fl;
+  }
+  uint32_t idx[8];
+  corner_indices(lv, l, pg, idx);
+  float* base = grad_table + (size_t)off * 2;
+  const float hs = 0.5f * scale;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int cx = c & 1, cy = (c >> 1) & 1, cz = (c >> 2) & 1;
+    const float wx = cx ? fr[0] : 1.f - fr[0], wy = cy ? fr[1] : 1.f - fr[1], wz = cz ? fr[2] : 1.f - fr[2];
+    const float w = wx * wy * wz;
+    const float dw = (cx ? eg[0] : -eg[0]) * (wy * wz) + (cy ? eg[1] : -eg[1]) * (wx * wz) + (cz ? eg[2] : -eg[2]) * (wx * wy);
+    const float k = hs * dw;
+    const float v0 = fmaf(k, q0, w * g0), v1 = fmaf(k, q1, w * g1);
+    if (v0 != 0.f || v1 != 0.f) red_add_v2(base + (size_t)idx[c] * 2, v0, v1);
+  }
+}
+
 // Loss seeds for one sample (nerf_runner.py:693-732, nerf_helpers.py:367-399). Inputs: network output (rgb logits,
 // sdf), normalised compositing weight w (already 0 for invalid samples), ray weight. Returns dL/draw (unscaled) and
 // accumulates the per-term loss values into acc[5] = {total, rgb(unused here), fs, sdf, fs_rgb}.

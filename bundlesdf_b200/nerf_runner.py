@@ -170,9 +170,8 @@ class NerfRunner:
         """nerf_runner.py:204-242: same modules, same creation order (=> same CPU-RNG initial weights for a given seed)."""
         device = device or self.device
         cfg = self.cfg
-        if cfg.get('eikonal_weight', 0) > 0:
-            raise NotImplementedError('eikonal_weight>0: the term is non-functional in the reference (train_loop renders with '
-                                      'get_normals=False, nerf_runner.py:686 -> KeyError at :736); not built yet (DESIGN.md row a15)')
+        if cfg.get('eikonal_weight', 0) > 0 and not (cfg['amp'] and cfg['N_samples'] + cfg['N_samples_around_depth'] <= 256):
+            raise NotImplementedError('eikonal_weight>0 is built for amp: true and N_samples + N_samples_around_depth <= 256 (DESIGN.md row a15)')
         if cfg.get('depth_weight', 0) > 0:
             raise NotImplementedError('depth_weight>0: dead code in the reference (uses an undefined `depth`, nerf_runner.py:718)')
         if cfg['N_importance'] > 0:
@@ -677,7 +676,7 @@ class NerfRunner:
         self.check_device_flags()
         l = self._step_buf['losses'].cpu().numpy()
         m = {'loss': float(l[0]), 'rgb_loss': float(l[1]), 'rgb0_loss': 0.0, 'fs_rgb_loss': float(l[4]), 'depth_loss': 0.0, 'depth_loss0': 0.0,
-             'fs_loss': float(l[2]), 'point_cloud_loss': 0.0, 'point_cloud_normal_loss': 0.0, 'sdf_loss': float(l[3]), 'eikonal_loss': 0.0,
+             'fs_loss': float(l[2]), 'point_cloud_loss': 0.0, 'point_cloud_normal_loss': 0.0, 'sdf_loss': float(l[3]), 'eikonal_loss': float(l[7]),
              'variation_loss': 0.0, 'truncation(meter)': self.get_truncation() / self.cfg['sc_factor'],
              'valid_samples': float(l[5]), 'valid_rays': float(l[6])}
         fa = self.models['feature_array']

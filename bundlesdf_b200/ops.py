@@ -120,7 +120,7 @@ class StepBuffers:
 
 
 LOSS_CFG_KEYS = ['sdf_lambda', 'neg_trunc_ratio', 'rgb_weight', 'fs_weight', 'empty_weight', 'trunc_weight', 'fs_sdf',
-                 'fs_rgb_weight', 'first_frame_weight']
+                 'fs_rgb_weight', 'first_frame_weight', 'eikonal_weight']
 
 
 def fill_step_cfg(sb, cfg, trunc):

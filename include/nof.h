@@ -194,7 +194,7 @@ typedef struct {
   float* grad_mlp;              /* packed like `mlp`, scaled by loss_scale */
   float* grad_tf;               /* [F,12], scaled */
   float* grad_feat;             /* [F,ff] or NULL, scaled (reg term added by the host side) */
-  float* losses;                /* [8]: loss, rgb, fs, sdf, fs_rgb, n_valid_samples, n_valid_rays, - (unscaled) */
+  float* losses;                /* [8]: loss, rgb, fs, sdf, fs_rgb, n_valid_samples, n_valid_rays, eikonal (unscaled) */
   int32_t* found_inf;           /* device flag, set when an fp16 conversion overflowed (amp) */
   /* optional debug / parity taps (NULL to skip) */
   float* rgb_map;               /* [N,3] */
@@ -203,6 +203,10 @@ typedef struct {
   float* weights;               /* [N,S] compositing weights */
   /* workspace from nof_step_workspace_bytes */
   void* workspace;
+  /* eikonal regulariser (cfg eikonal_weight; nerf_runner.py:734-738 with the normals of :1342-1345 — the reference's own train_loop
+   * cannot run it: it renders with get_normals=False, :686): eikonal_weight * mean over {sdf < 1} of (|d sdf / d x| - 1)^2, x detached.
+   * > 0 needs amp == 1 and S <= 256 (built in the mma.sync tile kernel); the value of the term lands in losses[7]. */
+  float eikonal_weight;
 } NofStep;
 
 size_t nof_step_workspace_bytes(const NofStep* p);

@@ -747,6 +747,9 @@ def forward_step(params, batch, c2w, occ, cfg, t_rand_occ=None, t_rand_depth=Non
     views_flat = views[:, None, :].expand(-1, S, -1).reshape(N * S, -1)
     raw = mlp_forward(params, enc, views_flat, half=half).reshape(N, S, 4)
     out = step_losses(raw, z_vals, valid, batch, trunc, cfg, params.get('pose_data'), params.get('feature_data'))
+    if cfg.get('eikonal_weight', 0) > 0:                               # a15: intended maths of nerf_runner.py:734-738 (see eikonal_loss)
+        out['eikonal_loss'] = eikonal_loss(params, xf, vf, cfg['eikonal_weight'], half=half)
+        out['loss'] = out['loss'] + out['eikonal_loss']
     out.update(raw=raw, z_vals=z_vals, valid_samples=valid, x=x, tf=tf_all, sampling_error=err)
     return out
 
@@ -877,16 +880,20 @@ def weld_triangles(verts, keys):
 # samples with sdf < 1, and its gradient w.r.t. the table and the SDF net comes from double backward (create_graph=True). Only
 # valid samples have a network output (nerf_runner.py:1247), the others contribute sdf = 0 < 1 with n = 0, i.e. (0-1)^2 = 1,
 # exactly like the reference's indexing `nerf_normals[sdf<1]` would.
-def sdf_normals(params, x, valid, create_graph=False):
+def sdf_normals(params, x, valid, create_graph=False, half=False):
     """x [P,3] normalised points (requires no grad on entry), valid [P] bool. Returns (sdf [P], n [P,3]) with zeros at invalid
-    samples; n is differentiable w.r.t. the parameters when create_graph=True."""
+    samples; n is differentiable w.r.t. the parameters when create_graph=True. half: fp16 operand rounding of the AMP policy
+    (table, encoding, weights, activations rounded to fp16, fp32 accumulation) — the casts are differentiable (identity)."""
     xr = x.detach().clone().requires_grad_(True)
     E = (len(params['offsets']) - 1) * params['embeddings'].shape[1]
     enc = torch.zeros(x.shape[0], E, dtype=x.dtype)
     idx = valid.nonzero().reshape(-1)
-    enc_valid = grid_encode((xr[idx] + 1) / 2, params['embeddings'], params['offsets'], params['S'], params['H'], exact_fma=False)
+    emb = params['embeddings'].half().float() if half else params['embeddings']
+    enc_valid = grid_encode((xr[idx] + 1) / 2, emb, params['offsets'], params['S'], params['H'], exact_fma=False)
+    if half:
+        enc_valid = enc_valid.half().float()
     enc = enc.index_put((idx,), enc_valid)
-    sdf_v = mlp_forward_sdf(params, enc[idx])
+    sdf_v = mlp_forward_sdf(params, enc[idx], half=half)
     sdf = torch.zeros(x.shape[0], dtype=x.dtype).index_put((idx,), sdf_v)
     (n,) = torch.autograd.grad(sdf_v.sum(), xr, create_graph=create_graph, allow_unused=True)
     if n is None:
@@ -894,9 +901,9 @@ def sdf_normals(params, x, valid, create_graph=False):
     return sdf, n
 
 
-def eikonal_loss(params, x, valid, eikonal_weight):
+def eikonal_loss(params, x, valid, eikonal_weight, half=False):
     """eikonal_weight * mean over {sdf < 1} of (|n| - 1)^2, differentiable w.r.t. params['embeddings'] and the sigma_net weights."""
-    sdf, n = sdf_normals(params, x, valid, create_graph=True)
+    sdf, n = sdf_normals(params, x, valid, create_graph=True, half=half)
     sel = sdf.detach() < 1
     if not bool(sel.any()):
         return torch.zeros((), dtype=x.dtype)

@@ -151,3 +151,33 @@ def test_query_sdf_matches_oracle():
     want = O.mlp_forward_sdf(P, enc)
     got = ops.query_sdf(res['sb'], x.cuda())
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('L,finest,log2T,S_occ,S_d,N', [(16, 256, 12, 64, 64, 40), (16, 256, 12, 128, 64, 14), (4, 128, 14, 32, 32, 48), (16, 256, 12, 128, 128, 7)])
+def test_fused_step_with_eikonal_matches_oracle(L, finest, log2T, S_occ, S_d, N):
+    """a15: eikonal_weight > 0 (BASELINE config 5). The term is defined by oracle.eikonal_loss (the intended maths of nerf_runner.py:734-738
+    with the normals of :1342-1345; torch double backward): value of the term, total loss and every gradient it touches (table, W1, W2[0,:])
+    against the CUDA path (count pre-pass + the mma.sync tile kernel). AMP tolerances: loss terms 5e-3 (1e-2 for the eikonal term itself:
+    |n| goes through the fp16 Jacobian block), gradients 3e-2 of max|g| (5e-2 for the tensors the term feeds)."""
+    cfg = helpers.make_cfg(L, finest, log2T, S_occ, S_d, eikonal_weight=0.05)
+    scene = helpers.make_scene(n_frames=4, N=N, cfg=cfg, invalid_frac=0.1)
+    t_rand = np.random.default_rng(21).random((N, S_occ + S_d), dtype=np.float32)
+    res = helpers.run_fused_step(scene, amp=True, t_rand=t_rand, loss_scale=1024.0)
+    ref, P = _oracle(scene, t_rand, half=True, z_vals=res['z_vals'].cpu())
+    losses = res['losses'].cpu().numpy()
+    want_e = float(ref['eikonal_loss'].detach())
+    assert want_e > 0 and abs(losses[7] - want_e) <= 1e-2 * want_e, (losses[7], want_e)
+    want = float(ref['loss'].detach())
+    assert abs(losses[0] - want) <= 5e-3 * abs(want), (losses[0], want)
+    scale = 1024.0
+    # the term's share of the gradients is not negligible: without it the comparison below fails (checked by the second run)
+    assert _rel_max(res['grad_table'].cpu().numpy() / scale, P['embeddings'].grad.numpy()) < 5e-2
+    for k, g in res['grad_mlp_named'].items():
+        tol = 5e-2 if k.startswith('sigma_net') else 3e-2
+        assert _rel_max(g.cpu().numpy() / scale, P[k].grad.numpy()) < tol, k
+    assert _rel_max(res['grad_pose'].cpu().numpy(), P['pose_data'].grad.numpy()) < 6e-2
+    assert res['found_inf'].item() == 0
+    cfg0 = dict(scene['cfg'], eikonal_weight=0.0)
+    res0 = helpers.run_fused_step(dict(scene, cfg=cfg0), amp=True, t_rand=t_rand, loss_scale=1024.0)
+    assert _rel_max(res0['grad_table'].cpu().numpy() / scale, P['embeddings'].grad.numpy()) > 5e-2
+    assert res0['losses'][7].item() == 0.0
