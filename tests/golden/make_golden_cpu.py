@@ -161,6 +161,20 @@ def main():
     torch.Tensor.cuda = lambda self, *a, **k: self            # DataLoader.__next__ calls .cuda()
     order = [next(dl).reshape(-1).numpy().copy() for _ in range(9)]
     sv('ref_py_misc.npz', dirs=dirs, K=K, tf=tfm, pts=pts, tp=tp, dl_order=np.stack(order))
+
+    # ---- 8. tool.py: scene normalisation (tool.py:18-39) and depth back-projection (Utils.py:219-231) of the reference itself
+    import importlib
+    tool = importlib.import_module('tool')
+    rng = np.random.default_rng(9)
+    cloud = np.concatenate([rng.normal([0.02, -0.01, 0.55], [0.04, 0.05, 0.09], size=(3000, 3)),      # the object
+                            rng.normal([0.40, 0.30, 0.90], 0.01, size=(60, 3))])                       # a detached blob DBSCAN must drop
+    t0, s0, k0 = tool.compute_translation_scales(cloud.copy(), cluster=True, eps=0.06, min_samples=1)
+    t1, s1, k1 = tool.compute_translation_scales(cloud.copy(), cluster=False)
+    depth = (rng.random((12, 16)) * 1.5).astype(np.float32)
+    depth[depth < 0.3] = 0.05
+    xyz = U.depth2xyzmap(depth, K)
+    sv('ref_py_tool.npz', cloud=cloud, translation_cluster=t0, sc_cluster=s0, keep_cluster=k0, translation_all=t1, sc_all=s1, keep_all=k1,
+       depth=depth, K=K, xyz=xyz, glcam_in_cvcam=U.glcam_in_cvcam)
     print('golden CPU fixtures written to', HERE)
 
 
