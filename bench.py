@@ -33,13 +33,13 @@ CONFIGS = {
     'C1': dict(frames=1, N=1024, S_occ=32, S_d=32, L=4, finest=128, log2T=22, pose=0, noise=False, stride=1),
     'C2': dict(frames=200, N=2048, S_occ=64, S_d=64, L=16, finest=256, log2T=19, pose=1, noise=False, stride=1),
     'C3': dict(frames=20, N=4096, S_occ=64, S_d=64, L=16, finest=256, log2T=19, pose=1, noise=True, stride=50),
-    'C5': dict(frames=300, N=8192, S_occ=128, S_d=64, L=16, finest=512, log2T=22, pose=1, noise=False, stride=1),
+    'C5': dict(frames=300, N=8192, S_occ=128, S_d=64, L=16, finest=512, log2T=22, pose=1, noise=False, stride=1, eik=0.1),
 }
 WORKLOAD = {
     'C1': 'C1: single 640x480 synthetic RGBD frame, 1024 rays x 64 samples, hash L=4, MLP 2x64/3x64',
     'C2': 'C2: milk-jug synthetic sequence, 200 frames 640x480, 2048 rays x 128 samples, hash L=16 T=2^19, MLP 2x64/3x64, 1xB200',
     'C3': 'C3: HO3D-shaped synthetic, 640x480, 1000-frame orbit, 20-frame memory pool, 4096 rays x 128 samples, pose refinement on',
-    'C5': 'C5: global-refine mode, 300 frames, 8192 rays x 192 samples, hash L=16 T=2^22',
+    'C5': 'C5: global-refine mode, 300 frames, 8192 rays x 192 samples, hash L=16 T=2^22, eikonal on (weight 0.1)',
 }
 
 
@@ -50,13 +50,13 @@ def make_cfg(c):
     from bundlesdf_b200 import synthetic as syn
     return syn.default_cfg(N_rand=c['N'], N_samples=c['S_occ'], N_samples_around_depth=c['S_d'], num_levels=c['L'], finest_res=c['finest'],
                            log2_hashmap_size=c['log2T'], optimize_poses=c['pose'], amp=True, n_step=2000, denoise_depth_use_octree_cloud=True,
-                           defer_table_update=DEFER_TABLE)
+                           defer_table_update=DEFER_TABLE, eikonal_weight=c.get('eik', 0.0))
 
 
 def algorithmic_bytes(c):
-    """64*L*C B/point with pose refinement (48*L*C without) + 60 B/ray."""
+    """64*L*C B/point with pose refinement (48*L*C without; + 16*L*C for the eikonal term's re-gather) + 60 B/ray."""
     P = c['N'] * (c['S_occ'] + c['S_d'])
-    per_pt = (64 if c['pose'] else 48) * c['L'] * 2
+    per_pt = ((64 if c['pose'] else 48) + (16 if c.get('eik', 0) > 0 else 0)) * c['L'] * 2
     return P * per_pt + c['N'] * 60
 
 
@@ -404,7 +404,7 @@ def measure_config(args, c, name, rank, world, local_rank, dev, with_kernel=True
            'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': N * 12 * 4, 'd2h_bytes_per_step': 32, 'steps': K, 'reps': e2e_reps,
                    'ms_per_step': 1e3 * t_e2e / K, 'block_ms_min': 1e3 * min(e2e_blocks), 'block_ms_max': 1e3 * max(e2e_blocks)},
            'ray_pool': int(runner.rays.shape[0]), 'setup_s': round(t_setup, 1), 'n_params': n_params}
-    launches_per_step = (8 if DEFER_TABLE else 6)           # prologue, ray march, operand pack, fused step, pose backward, Adam (1 | 3)
+    launches_per_step = (8 if DEFER_TABLE else 6) + (1 if c.get('eik', 0) > 0 else 0)   # prologue, ray march, operand pack, fused step, pose backward, Adam (1 | 3) [+ eikonal count pass]
     res['gpu_launches'] = launches_per_step * K * reps
     if not with_kernel:
         return res
@@ -471,6 +471,7 @@ def main():
     def config_of(cc, nm):
         return {'workload': WORKLOAD[nm], 'rays_per_step': cc['N'], 'samples_per_ray': cc['S_occ'] + cc['S_d'], 'hash_levels': cc['L'],
                 'log2_hashmap_size': cc['log2T'], 'finest_res': cc['finest'], 'frames': cc['frames'], 'amp': True, 'optimize_poses': bool(cc['pose']),
+                'eikonal_weight': cc.get('eik', 0.0),
                 'defer_table_update': DEFER_TABLE, 'graph_block_steps': 10,
                 'parallelism': f'{world} independent sequence(s), one per GPU',
                 'l2_policy': 'inputs larger than L2 are not claimed: the fp16 table (17.4 MB at C2/C3) is L2-resident by design; every step draws a '
