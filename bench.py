@@ -543,10 +543,12 @@ def main():
 def reference_cuda_column(c, name):
     """SURVEY.md 8(d) second comparison column: the reference's OWN train_loop (nerf_runner.py:679-852) on its own compiled CUDA
     extensions (oracle/_ref) on this B200. Test infrastructure timed in the cpu_baseline leg only; None when oracle/_ref is absent."""
+    import contextlib
     try:
         sys.path.insert(0, os.path.join(REPO, 'oracle'))
-        import ref_train_loop
-        return ref_train_loop.time_reference(c, name)
+        with contextlib.redirect_stdout(sys.stderr):      # the reference prints while it builds its models; stdout carries ONE JSON line
+            import ref_train_loop
+            return ref_train_loop.time_reference(c, name)
     except Exception as e:      # the checker is optional
         return {'unavailable': repr(e)[:300]}
 

@@ -305,15 +305,31 @@ __device__ __forceinline__ void scatter_level_eik(float* grad_table, const Level
   corner_indices(lv, l, pg, idx);
   float* base = grad_table + (size_t)off * 2;
   const float hs = 0.5f * scale;
+  const bool pairable = (off & 1u) == 0u;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int cx = c & 1, cy = (c >> 1) & 1, cz = (c >> 2) & 1;
-    const float wx = cx ? fr[0] : 1.f - fr[0], wy = cy ? fr[1] : 1.f - fr[1], wz = cz ? fr[2] : 1.f - fr[2];
-    const float w = wx * wy * wz;
-    const float dw = (cx ? eg[0] : -eg[0]) * (wy * wz) + (cy ? eg[1] : -eg[1]) * (wx * wz) + (cz ? eg[2] : -eg[2]) * (wx * wy);
-    const float k = hs * dw;
-    const float v0 = fmaf(k, q0, w * g0), v1 = fmaf(k, q1, w * g1);
-    if (v0 != 0.f || v1 != 0.f) red_add_v2(base + (size_t)idx[c] * 2, v0, v1);
+  for (int k = 0; k < 4; ++k) {                               // (y, z) pairs; the x / x+1 corners share one 16-byte reduction when adjacent
+    const int cy = k & 1, cz = k >> 1;
+    const float wy = cy ? fr[1] : 1.f - fr[1], wz = cz ? fr[2] : 1.f - fr[2];
+    const float wyz = wy * wz;
+    const float dyz = (cy ? eg[1] : -eg[1]) * wz + (cz ? eg[2] : -eg[2]) * wy;       // d(wy wz)/df . g over y, z
+    float v[2][2];
+#pragma unroll
+    for (int cx = 0; cx < 2; ++cx) {
+      const float wx = cx ? fr[0] : 1.f - fr[0];
+      const float w = wx * wyz;
+      const float dw = (cx ? eg[0] : -eg[0]) * wyz + wx * dyz;
+      const float kq = hs * dw;
+      v[cx][0] = fmaf(kq, q0, w * g0);
+      v[cx][1] = fmaf(kq, q1, w * g1);
+    }
+    const uint32_t e0 = idx[2 * k], e1 = idx[2 * k + 1];
+    if ((e0 ^ e1) == 1u && pairable) {
+      const bool sw = (e0 & 1u) != 0u;                        // e0 is the odd entry: swap the halves
+      red_add_v4(base + (size_t)(e0 & ~1u) * 2, sw ? v[1][0] : v[0][0], sw ? v[1][1] : v[0][1], sw ? v[0][0] : v[1][0], sw ? v[0][1] : v[1][1]);
+    } else {
+      red_add_v2(base + (size_t)e0 * 2, v[0][0], v[0][1]);
+      red_add_v2(base + (size_t)e1 * 2, v[1][0], v[1][1]);
+    }
   }
 }
 

@@ -102,14 +102,19 @@ def time_reference(c, name, steps=10, warmup=3):
     ours, _ = bench.build_runner(c, seed=0, device=dev, eager=True)
     ref = build_reference_runner(ours)
     N = c['N']
-    for _ in range(warmup):
-        ref.train_loop(next(ref.data_loader))
+    def one():
+        batch = next(ref.data_loader)
+        # torch >= 2 refuses to index the CPU id tensor with the CUDA mask of render_rays (nerf_runner.py:1075; torch 1.11, which the
+        # reference pins, accepted it): hand the ids over on the batch's device. Nothing else of the loop is touched.
+        ref.data_loader.batch_ray_ids = ref.data_loader.batch_ray_ids.to(batch.device)
+        ref.train_loop(batch)
         ref.global_step += 1
+    for _ in range(warmup):
+        one()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        ref.train_loop(next(ref.data_loader))
-        ref.global_step += 1
+        one()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return {'value': N * steps / dt, 'unit': 'rays/s', 'ms_per_step': 1e3 * dt / steps, 'steps': steps, 'warmup': warmup, 'kind': 'reference-cuda',

