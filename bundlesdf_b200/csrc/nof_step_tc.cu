@@ -1,7 +1,9 @@
 // Fused forward + loss + backward of one train step, AMP policy, tcgen05 edition (tile PT = 128 points, S <= 128).
 //
-// Same structure as nof_step_amp.cu (two threads per point, gather / compositing / seeds / scatter identical), but the
-// ten chained GEMMs of the MLP forward and dgrad run on the 5th-generation tensor cores:
+// Same structure as nof_step_amp.cu (two threads per point, every warp walks the phases of a tile together: one instruction stream per SM
+// at a time, which is what keeps this ~8 k-instruction kernel inside the instruction cache — see profiles/README.md for what happens when
+// the phases run as concurrent warp roles instead), but the ten chained GEMMs of the MLP forward and dgrad run on the 5th-generation
+// tensor cores:
 //   * one elected thread issues tcgen05.mma (M=128 = the whole tile, N = layer width, K = 16 per instruction) with both
 //     operands read straight from shared memory through UMMA descriptors; the accumulator lives in TMEM (64 columns);
 //   * completion is signalled by tcgen05.commit on an mbarrier; every thread then pulls ITS row (32 columns of it) out of
@@ -13,142 +15,50 @@
 //     generations overlap.
 // Ablation on B200 (profiles/README.md): the mma.sync + ldmatrix MLP phases cost 174 of 286 us per C2 launch; this kernel
 // replaces 156 of the 264 mma.sync and 152 of the 240 ldmatrix per warp and tile by 26 tcgen05.mma per CTA and tile.
-#include "nof_step_common.cuh"
+#include "nof_mlp_image.cuh"
 
 namespace nof {
 namespace tc {
+using namespace prim;
+using img::KG;
+using img::VPAD;
 
-// ------------------------------------------------------------------------------------------------ primitives
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ldsm_x4_t(uint32_t r[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void mma16816(float c[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Bounded wait: never hangs the GPU. Returns false on timeout (the caller raises the device error flag).
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t phase) {
-  const uint32_t addr = smem_u32(bar);
+// Bounded wait with the polling loop INLINE: every thread of the CTA waits ten times per tile with ~60 live registers (the weight-gradient
+// accumulators); an out-of-line call there costs more than the loop's footprint saves in this lock-step kernel (unlike nof_step_ws.cu).
+__device__ __forceinline__ bool mbar_wait_inl(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
-  for (int it = 0; it < (1 << 22); ++it) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(phase)
-        : "memory");
-    if (ok) return true;
-  }
+  for (int it = 0; it < (1 << 22); ++it)
+    if (mbar_try(bar, parity)) return true;
   return false;
 }
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, SWIZZLE_NONE (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-// version=1 [46,48), layout_type=0 [61,64)).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
-         (1ull << 46);
-}
-// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=f16 (0), a_major bit15, b_major bit16,
-// N>>3 at [17,23), M>>4 at [24,29).
-__device__ __forceinline__ constexpr uint32_t umma_idesc(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      :
-      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-template <int N> struct TmemLd;
-template <> struct TmemLd<8> {
-  static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-  }
-};
-template <> struct TmemLd<16> {
-  static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-  }
-};
-template <> struct TmemLd<32> {
-  static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
-    TmemLd<16>::ld(taddr, v);
-    TmemLd<16>::ld(taddr + 16, v + 16);
-  }
-};
-
-// ------------------------------------------------------------------------------------------------ core-matrix layout
-// element (r, k) of an [R x K] fp16 matrix: 8 rows x 8 columns (16 bytes per row) form one contiguous 128-byte core matrix;
-// core matrices are ordered k-chunk fastest: byte offset = (r/8)*(K*16) + (k/8)*128 + (r%8)*16 + (k%8)*2.
-__device__ __forceinline__ uint32_t cm_off(int r, int k, int K) { return (uint32_t)((r >> 3) * (K * 16) + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2); }
 
 constexpr int PT = 128, NT = 256, NWARP = 8;
 constexpr int DES = PT + PT / 8;                 // padded point stride of the transposed dEnc / z arrays: index pt + pt/8
 __device__ __forceinline__ int des_idx(int pt) { return pt + (pt >> 3); }
 
+struct RayT : RayS {                          // + the per-ray share of the colour net (nof_mlp_image.cuh)
+  float vb[64];                               // W3[:, views] . views
+  float cr[64];                               // sum over the ray's samples of dY3 -> d views, dW3[:, views]
+};
+
 struct Plan {
-  int w1, w2, w3, w4, w5, bias, x0, x1, xc, x3, x4, d_o, out, zs, rays, lv, bar, tmem, total;
+  int w1, w2, w3, w4, w5, bias, w3v, lv, img_bytes, x0, x1, xc, x3, x4, d_o, out, zs, rays, bar, tmem, total;
 };
 __host__ __device__ inline Plan make_plan(int KE) {
   Plan s;
-  int o = 0;
+  const img::ImagePlan ip = img::make_image_plan(KE);
+  s.w1 = ip.w1; s.w2 = ip.w2; s.w3 = ip.w3g; s.w4 = ip.w4; s.w5 = ip.w5; s.bias = ip.bias; s.w3v = ip.w3v; s.lv = ip.lv; s.img_bytes = ip.bytes;
+  int o = ip.bytes;
   auto take = [&](int bytes) { int r = o; o += (bytes + 127) / 128 * 128; return r; };
-  s.w1 = take(64 * KE * 2);
-  s.w2 = take(16 * 64 * 2);
-  s.w3 = take(64 * KC * 2);
-  s.w4 = take(64 * 64 * 2);
-  s.w5 = take(16 * 64 * 2);
-  s.bias = take(216 * 4);
   s.x0 = take(PT * KE * 2);
   s.x1 = take(PT * 64 * 2);
-  s.xc = take(PT * KC * 2);
+  s.xc = take(PT * KG * 2);                  // geo features (15 + pad): the only per-sample input of the colour net
   s.x3 = take(PT * 64 * 2);                 // x3|x4 also hold dEnc fp32 [KE][DES] (transposed) at the end of the backward
   s.x4 = take(PT * 64 * 2);
   s.d_o = take(PT * 16 * 2);
   s.out = take(PT * 4 * 4);
   s.zs = take(5 * DES * 4);                  // z, valid flag and u[3] of every point, in the scatter's padded order
-  s.rays = take(MAX_R * (int)sizeof(RayS));
-  s.lv = take((int)sizeof(LevelS));
+  s.rays = take(MAX_R * (int)sizeof(RayT));
   s.bar = take(64);                          // [0] TMA staging barrier, [1] MMA completion barrier
   s.tmem = take(16);
   s.total = o;
@@ -156,15 +66,20 @@ __host__ __device__ inline Plan make_plan(int KE) {
 }
 
 // wgrad on mma.sync reading core-matrix buffers (same balanced split as nof_step_amp.cu): dW[strip*16..+16][nt0*8..] += dY^T X
-template <int NTU>
+// RSUM: the column sums of dY (which the bias gradient needs anyway) are also added, ray by ray (ks_per_ray k-steps each), to cr of
+// the tile's rays: lanes with t4 == 0 hold rows g8 and g8 + 8 of the strip.
+// and dW3[:, views] += c_r (x) views goes into w3v (rows g8 / g8 + 8 of the strip, view columns t4, t4 + 4, ...: every lane of a quad holds the
+// same row sums, so the four lanes split the columns).
+template <int NTU, bool RSUM = false>
 __device__ __forceinline__ void wgrad_item(uint32_t dY, int Ky, uint32_t X, int Kx, int strip, int nt0, float (*acc)[4], float* bias2,
-                                           bool do_bias, int lane) {
+                                           bool do_bias, int lane, RayT* rays = nullptr, int ks_per_ray = 8, float (*w3v)[2] = nullptr, int V = 0) {
 #ifdef NOF_EXP_NO_WGRAD
   return;
 #endif
   const uint32_t ones = 0x3C003C00u;
   const int pa = (lane & 7) + (lane >> 4) * 8, oa = strip * 16 + ((lane >> 3) & 1) * 8;       // A: rows p, cols o (dY^T)
   const int pb = (lane & 7) + ((lane >> 3) & 1) * 8, ib = (lane >> 4) * 8;                      // B: rows p, cols i
+  float r0 = 0.f, r1 = 0.f;
   for (int ks = 0; ks < PT / 16; ++ks) {
     uint32_t a[4];
     ldsm_x4_t(a, dY + cm_off(ks * 16 + pa, oa, Ky));
@@ -180,6 +95,27 @@ __device__ __forceinline__ void wgrad_item(uint32_t dY, int Ky, uint32_t X, int 
       mma16816(t, a, ones, ones);
       bias2[0] += t[0];
       bias2[1] += t[2];
+      if (RSUM) {
+        r0 += t[0];
+        r1 += t[2];
+        if ((ks + 1) % ks_per_ray == 0) {
+          RayT& rq = rays[ks / ks_per_ray];
+          if ((lane & 3) == 0) {                                // one strip <-> one warp: plain stores, no atomics
+            rq.cr[strip * 16 + (lane >> 2)] = r0;
+            rq.cr[strip * 16 + (lane >> 2) + 8] = r1;
+          }
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int v = (lane & 3) + 4 * k;
+            if (v < V) {
+              const float hv = __half2float(__float2half_rn(rq.views[v]));
+              w3v[k][0] = fmaf(r0, hv, w3v[k][0]);
+              w3v[k][1] = fmaf(r1, hv, w3v[k][1]);
+            }
+          }
+          r0 = r1 = 0.f;
+        }
+      }
     }
   }
 }
@@ -193,7 +129,8 @@ struct WSplit {
 };
 template <int CNT>
 __device__ __forceinline__ void flush_item(float* G, int wofs, int bofs, int ncols, int nrows, int strip, int nt0, const float (*acc)[4],
-                                           const float* bias2, bool has_bias, int g8, int t4) {
+                                           const float* bias2, bool has_bias, int g8, int t4, int ld = -1, int kofs = 0) {
+  if (ld < 0) ld = ncols;
 #pragma unroll
   for (int nt = 0; nt < CNT; ++nt)
 #pragma unroll
@@ -201,7 +138,7 @@ __device__ __forceinline__ void flush_item(float* G, int wofs, int bofs, int nco
       const int o = strip * 16 + g8 + h * 8, i = (nt0 + nt) * 8 + 2 * t4;
       const float v0 = acc[nt][h * 2], v1 = acc[nt][h * 2 + 1];
       if (o >= nrows || i >= ncols) continue;
-      const size_t e = (size_t)wofs + (size_t)o * ncols + i;
+      const size_t e = (size_t)wofs + (size_t)o * ld + kofs + i;
       if (i + 1 < ncols && (reinterpret_cast<uintptr_t>(G + e) & 7u) == 0u) {                       // the fragment's two columns in one 8-byte reduction
         if (v0 != 0.f || v1 != 0.f) red_add_v2(G + e, v0, v1);
       } else {
@@ -243,44 +180,6 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, int
   umma_commit(bar);
 }
 
-// ------------------------------------------------------------------------------------------------ operand packing
-// fp32 packed parameters (nof_mlp_param_offsets order) -> the kernel's shared-memory image [W1 W2 W3 W4 W5 | biases]: fp16
-// weights in core-matrix order, zero padding, biases rounded through fp16 like torch autocast. One tiny kernel per step; the
-// 296 step CTAs then fetch the 21.5 KB image with one TMA bulk copy each instead of converting 9.6k weights each.
-template <int KE>
-__global__ void __launch_bounds__(256) pack_mlp_kernel(const StepArgs a) {
-  const Plan sp = make_plan(KE);
-  unsigned char* out = static_cast<unsigned char*>(a.wpack);      // image offset 0 == plan offset sp.w1 (== 0)
-  const int gid = blockIdx.x * 256 + threadIdx.x;
-  if (gid == 0) *reinterpret_cast<int*>(out + kWPackBytes - 16) = 0;                 // tile ticket of the step kernel
-  if (gid < 8) a.p.losses[gid] = 0.f;                                                // per-step results start from zero
-  if (a.p.grad_tf) for (int i = gid; i < a.p.F * 12; i += gridDim.x * 256) a.p.grad_tf[i] = 0.f;
-  const float* P = a.p.mlp;
-  const int o = gid * 4;                                          // one 32-bit word of the image per thread: gather form, no zero pass
-  if (o < sp.bias) {
-    int base, rows, kreal, kpad, po;
-    if (o >= sp.w5) { base = sp.w5; rows = 3; kreal = 64; kpad = 64; po = a.po[8]; }
-    else if (o >= sp.w4) { base = sp.w4; rows = 64; kreal = 64; kpad = 64; po = a.po[6]; }
-    else if (o >= sp.w3) { base = sp.w3; rows = 64; kreal = a.V + 15; kpad = KC; po = a.po[4]; }
-    else if (o >= sp.w2) { base = sp.w2; rows = 16; kreal = 64; kpad = 64; po = a.po[2]; }
-    else { base = sp.w1; rows = 64; kreal = a.E; kpad = KE; po = a.po[0]; }
-    const int rel = o - base, rg = rel / (kpad * 16), rem = rel % (kpad * 16);
-    const int n = rg * 8 + (rem % 128) / 16, k = (rem / 128) * 8 + (rem % 16) / 2;          // inverse of cm_off
-    const float v0 = (n < rows && k < kreal) ? P[po + n * kreal + k] : 0.f;
-    const float v1 = (n < rows && k + 1 < kreal) ? P[po + n * kreal + k + 1] : 0.f;
-    *reinterpret_cast<uint32_t*>(out + o) = pack_h2(v0, v1);
-  } else if (o < sp.x0) {
-    const int j = (o - sp.bias) / 4;
-    float v = 0.f;
-    if (j < 64) v = P[a.po[1] + j];
-    else if (j < 80) v = P[a.po[3] + j - 64];
-    else if (j < 144) v = P[a.po[5] + j - 80];
-    else if (j < 208) v = P[a.po[7] + j - 144];
-    else if (j < 211) v = P[a.po[9] + j - 208];
-    *reinterpret_cast<float*>(out + o) = __half2float(__float2half_rn(v));
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int KE_>
 __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
@@ -290,8 +189,9 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   float* sB = reinterpret_cast<float*>(smem + sp.bias);
   float* sOut = reinterpret_cast<float*>(smem + sp.out);
   float* sZ = reinterpret_cast<float*>(smem + sp.zs);
-  RayS* sRay = reinterpret_cast<RayS*>(smem + sp.rays);
-  LevelS& lv = *reinterpret_cast<LevelS*>(smem + sp.lv);
+  RayT* sRay = reinterpret_cast<RayT*>(smem + sp.rays);
+  const LevelS& lv = *reinterpret_cast<const LevelS*>(smem + sp.lv);
+  const __half* sW3v = reinterpret_cast<const __half*>(smem + sp.w3v);
   uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem + sp.bar);
   uint64_t* bar_mma = bar_tma + 1;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + sp.tmem);
@@ -321,24 +221,24 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
   // MLP operands: already fp16, core-matrix ordered and zero-padded (pack_mlp_kernel) — one bulk copy, no conversion
-  const uint32_t pack_bytes = (uint32_t)(sp.x0 - sp.w1);
+  const uint32_t pack_bytes = (uint32_t)sp.img_bytes;
   if (tid == 0) {
     mbar_expect_tx(bar_tma, pack_bytes);
     tma_bulk_g2s(smem + sp.w1, a.wpack, pack_bytes, bar_tma);
   }
-  init_levels(lv, a);
-  bool tc_ok = mbar_wait(bar_tma, 0);
+  bool tc_ok = mbar_wait_inl(bar_tma, 0);
   fence_async_smem();
   __syncthreads();
 
   using S1 = WSplit<4, KE / 8>;
   using S2 = WSplit<1, 8>;
-  using S3 = WSplit<4, KC / 8>;
+  using S3 = WSplit<4, KG / 8>;
   using S4 = WSplit<4, 8>;
   using S5 = WSplit<1, 8>;
   float wg1[S1::CNT][4], wg2[S2::CNT][4], wg3[S3::CNT][4], wg4[S4::CNT][4], wg5[S5::CNT][4];
   float wb1[2] = {0.f, 0.f}, wb2[2] = {0.f, 0.f}, wb3[2] = {0.f, 0.f}, wb4[2] = {0.f, 0.f}, wb5[2] = {0.f, 0.f};
   zero_acc<S1::CNT>(wg1); zero_acc<S2::CNT>(wg2); zero_acc<S3::CNT>(wg3); zero_acc<S4::CNT>(wg4); zero_acc<S5::CNT>(wg5);
+  float w3v[5][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};       // dW3[:, views] rows g8 / g8+8 of this warp's strip, columns t4 + 4k
   float loss_acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   float n_valid_s = 0.f, n_valid_r = 0.f;
   bool overflow = false;
@@ -360,7 +260,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
 #ifdef NOF_EXP_NO_TC
     return;
 #endif
-    tc_ok &= mbar_wait(bar_mma, phase);
+    tc_ok &= mbar_wait_inl(bar_mma, phase);
     phase ^= 1u;
     tc_fence_after();
   };
@@ -382,7 +282,17 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
     if (tid == NT - 1) *s_next = (int)gridDim.x + atomicAdd(tile_ticket, 1);
     __syncthreads();
     grp = *s_next;                                          // the NEXT tile (this one's rays are already staged)
-    const RayS& rs = sRay[rl];
+    // the rays' share of the colour net's first layer (their view / frame-feature inputs are the same for every sample): W3[:, views] . views,
+    // on the fp16-rounded inputs autocast would feed; read as a per-ray bias by the layer-3 epilogue, several barriers from here
+    for (int i = tid; i < R * 64; i += NT) {
+      RayT& rq = sRay[i >> 6];
+      const int o = i & 63;
+      float acc = 0.f;
+      for (int v = 0; v < V; ++v) acc = fmaf(__half2float(sW3v[o * VPAD + v]), __half2float(__float2half_rn(rq.views[v])), acc);
+      rq.vb[o] = acc;
+      rq.cr[o] = 0.f;
+    }
+    const RayT& rs = sRay[rl];
     const bool active = rs.active && sidx < S;
     const float z = active ? a.p.z_vals[(size_t)rs.ray * S + sidx] : 0.f;
     float pc[3], x[3], u[3];
@@ -404,19 +314,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
         if (anyv) atomicOr(&sRay[rl].anyvalid, 1);
       }
     }
-    // ============ 2. colour-net input row (views; geo comes from L2) and this thread's half of the gather
-    if (!owner) {
-#pragma unroll
-      for (int ch = 0; ch < KC / 8; ++ch) {
-        uint32_t w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = ch * 8 + 2 * j;
-          w[j] = pack_h2(k < V ? rs.views[k] : 0.f, k + 1 < V ? rs.views[k + 1] : 0.f);
-        }
-        *reinterpret_cast<uint4*>(pXC + cm_off(pt, ch * 8, KC)) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    }
+    // ============ 2. this thread's half of the gather
     if (valid) {
 #pragma unroll 2
       for (int l = l_beg; l < l_end; ++l) {
@@ -465,12 +363,13 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
         const int col = half * 8 + j;
         const __half hv = __float2half_rn(v[j] + sB[64 + col]);
         if (col == 0) sOut[pt * 4 + 3] = __half2float(hv);
-        else *reinterpret_cast<__half*>(pXC + cm_off(pt, V + col - 1, KC)) = hv;
+        else *reinterpret_cast<__half*>(pXC + cm_off(pt, col - 1, KG)) = hv;
       }
+      if (!owner) *reinterpret_cast<__half*>(pXC + cm_off(pt, 15, KG)) = __float2half_rn(0.f);
     }
     sync_for_mma();
-    // ---- L3: (V+15 padded 32) -> 64, ReLU
-    if (tid == 0) issue_gemm<64, KC, 0>(tmem, aXC, KC, aW3, KC, bar_mma);
+    // ---- L3: geo 15 (+ the ray's view / feature share as a bias) -> 64, ReLU
+    if (tid == 0) issue_gemm<64, KG, 0>(tmem, aXC, KG, aW3, KG, bar_mma);
     mma_wait();
     {
       float v[32];
@@ -481,7 +380,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = half * 32 + ch * 8 + 2 * j;
-          w[j] = pack_h2(fmaxf(v[ch * 8 + 2 * j] + sB[80 + c], 0.f), fmaxf(v[ch * 8 + 2 * j + 1] + sB[80 + c + 1], 0.f));
+          w[j] = pack_h2(fmaxf(v[ch * 8 + 2 * j] + sB[80 + c] + rs.vb[c], 0.f), fmaxf(v[ch * 8 + 2 * j + 1] + sB[80 + c + 1] + rs.vb[c + 1], 0.f));
         }
         *reinterpret_cast<uint4*>(pX3 + cm_off(pt, half * 32 + ch * 8, 64)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
@@ -579,13 +478,13 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
       for (int ch = 0; ch < 4; ++ch) {
         unsigned char* p = pX4 + cm_off(pt, half * 32 + ch * 8, 64);
         const uint4 m = *reinterpret_cast<const uint4*>(p);
-        const __half2* mh = reinterpret_cast<const __half2*>(&m);
+        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
         uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float v0 = __low2float(mh[j]) > 0.f ? v[ch * 8 + 2 * j] : 0.f, v1 = __high2float(mh[j]) > 0.f ? v[ch * 8 + 2 * j + 1] : 0.f;
-          overflow |= !(fabsf(v0) <= 65504.f) || !(fabsf(v1) <= 65504.f);
-          o[j] = pack_h2(v0, v1);
+        for (int j = 0; j < 4; ++j) {                         // packed: round the pair, mask it with (activation > 0), test the exponents
+          const uint32_t keep = __hgt2_mask(*reinterpret_cast<const __half2*>(&mw[j]), __float2half2_rn(0.f));
+          o[j] = pack_h2(v[ch * 8 + 2 * j], v[ch * 8 + 2 * j + 1]) & keep;
+          overflow |= ((o[j] & 0x7C00u) == 0x7C00u) || ((o[j] & 0x7C000000u) == 0x7C000000u);
         }
         *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
       }
@@ -605,35 +504,33 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
       for (int ch = 0; ch < 4; ++ch) {
         unsigned char* p = pX3 + cm_off(pt, half * 32 + ch * 8, 64);
         const uint4 m = *reinterpret_cast<const uint4*>(p);
-        const __half2* mh = reinterpret_cast<const __half2*>(&m);
+        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
         uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float v0 = __low2float(mh[j]) > 0.f ? v[ch * 8 + 2 * j] : 0.f, v1 = __high2float(mh[j]) > 0.f ? v[ch * 8 + 2 * j + 1] : 0.f;
-          overflow |= !(fabsf(v0) <= 65504.f) || !(fabsf(v1) <= 65504.f);
-          o[j] = pack_h2(v0, v1);
+        for (int j = 0; j < 4; ++j) {                         // packed: round the pair, mask it with (activation > 0), test the exponents
+          const uint32_t keep = __hgt2_mask(*reinterpret_cast<const __half2*>(&mw[j]), __float2half2_rn(0.f));
+          o[j] = pack_h2(v[ch * 8 + 2 * j], v[ch * 8 + 2 * j + 1]) & keep;
+          overflow |= ((o[j] & 0x7C00u) == 0x7C00u) || ((o[j] & 0x7C000000u) == 0x7C000000u);
         }
         *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
     sync_for_mma();                                         // dY3 visible
-    // ---- layer 3: dgrad -> [dviews | dgeo | pad], wgrad dY3^T XC
-    if (tid == 0) issue_gemm<KC, 64, 1>(tmem, aX3, 64, aW3, KC, bar_mma);
+    // ---- layer 3: dgrad -> dgeo (the view part needs no per-sample dgrad), wgrad dY3^T XG + the per-ray column sums of dY3
+    if (tid == 0) issue_gemm<KG, 64, 1>(tmem, aX3, 64, aW3, KG, bar_mma);
     if (warp < S3::ITEMS)
-      wgrad_item<S3::CNT>(aX3, 64, aXC, KC, warp / S3::GROUPS, (warp % S3::GROUPS) * S3::CNT, wg3, wb3, (warp % S3::GROUPS) == 0, lane);
+      wgrad_item<S3::CNT, true>(aX3, 64, aXC, KG, warp / S3::GROUPS, (warp % S3::GROUPS) * S3::CNT, wg3, wb3, (warp % S3::GROUPS) == 0, lane, sRay,
+                                Sp / 16, w3v, V);
     mma_wait();
     {
-      float v[16];
-      TmemLd<16>::ld(trow + half * 16, v);
+      float v[8];
+      TmemLd<8>::ld(trow + half * 8, v);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = half * 16 + j;
-        if (col < V) {                                       // warp-uniform: all 32 rows of the warp belong to one ray
-          const float s = warp_sum(v[j]);
-          if (lane == 0 && s != 0.f) atomicAdd(&sRay[rl].dviews[col], s);
-        } else if (col < V + 15) {
+      for (int j = 0; j < 8; ++j) {
+        const int col = half * 8 + j;
+        if (col < 15) {
           overflow |= !(fabsf(v[j]) <= 65504.f);
-          *reinterpret_cast<__half*>(pDO + cm_off(pt, 1 + (col - V), 16)) = __float2half_rn(v[j]);
+          *reinterpret_cast<__half*>(pDO + cm_off(pt, 1 + col, 16)) = __float2half_rn(v[j]);
         }
       }
       if (owner) *reinterpret_cast<__half*>(pDO + cm_off(pt, 0, 16)) = __float2half_rn(dsdf_s);
@@ -652,13 +549,13 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
       for (int ch = 0; ch < 4; ++ch) {
         unsigned char* p = pX1 + cm_off(pt, half * 32 + ch * 8, 64);
         const uint4 m = *reinterpret_cast<const uint4*>(p);
-        const __half2* mh = reinterpret_cast<const __half2*>(&m);
+        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
         uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float v0 = __low2float(mh[j]) > 0.f ? v[ch * 8 + 2 * j] : 0.f, v1 = __high2float(mh[j]) > 0.f ? v[ch * 8 + 2 * j + 1] : 0.f;
-          overflow |= !(fabsf(v0) <= 65504.f) || !(fabsf(v1) <= 65504.f);
-          o[j] = pack_h2(v0, v1);
+        for (int j = 0; j < 4; ++j) {                         // packed: round the pair, mask it with (activation > 0), test the exponents
+          const uint32_t keep = __hgt2_mask(*reinterpret_cast<const __half2*>(&mw[j]), __float2half2_rn(0.f));
+          o[j] = pack_h2(v[ch * 8 + 2 * j], v[ch * 8 + 2 * j + 1]) & keep;
+          overflow |= ((o[j] & 0x7C00u) == 0x7C00u) || ((o[j] & 0x7C000000u) == 0x7C000000u);
         }
         *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
       }
@@ -785,22 +682,33 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
       }
     }
     __syncthreads();
-    if (tid < R && sRay[tid].active) {
-      RayS& r2 = sRay[tid];
-      if (a.p.grad_feat) {
-        for (int j = 0; j < a.p.ff; ++j)
-          if (r2.dviews[j] != 0.f) red_add(a.p.grad_feat + (size_t)r2.frame * a.p.ff + j, r2.dviews[j]);
+    // rays of this tile: d views = W3[:, views]^T c_r -> frame-feature gradient and (through the SH Jacobian) the pose. Warp w looks after
+    // ray w: lane v computes column v (64 multiply-adds, no shuffles), lane 0 finishes.
+    if (warp < R && sRay[warp].active && (a.p.grad_feat || (a.p.need_pose_grad && sRay[warp].frame != 0))) {
+      RayT& r2 = sRay[warp];
+      if (lane < V) {
+        float acc = 0.f;
+#pragma unroll 8
+        for (int o = 0; o < 64; ++o) acc = fmaf(r2.cr[o], __half2float(sW3v[o * VPAD + lane]), acc);
+        r2.dviews[lane] = acc;
       }
-      if (a.p.need_pose_grad && r2.frame != 0) {
-        float gd[3];
-        sh3_backward(r2.dw, r2.dviews + a.p.ff, gd);
+      __syncwarp();
+      if (lane == 0) {
+        if (a.p.grad_feat) {
+          for (int j = 0; j < a.p.ff; ++j)
+            if (r2.dviews[j] != 0.f) red_add(a.p.grad_feat + (size_t)r2.frame * a.p.ff + j, r2.dviews[j]);
+        }
+        if (a.p.need_pose_grad && r2.frame != 0) {
+          float gd[3];
+          sh3_backward(r2.dw, r2.dviews + a.p.ff, gd);
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+          for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const float v = gd[i] * r2.u[j];
-            if (v != 0.f) red_add(a.p.grad_tf + (size_t)r2.frame * 12 + i * 4 + j, v);
-          }
+            for (int j = 0; j < 3; ++j) {
+              const float vv = gd[i] * r2.u[j];
+              if (vv != 0.f) red_add(a.p.grad_tf + (size_t)r2.frame * 12 + i * 4 + j, vv);
+            }
+        }
       }
     }
     __syncthreads();
@@ -815,7 +723,18 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
     if (warp < S2::ITEMS)
       flush_item<S2::CNT>(G, a.po[2], a.po[3], 64, 16, 0, (warp % S2::GROUPS) * S2::CNT, wg2, wb2, (warp % S2::GROUPS) == 0, g8, t4);
     if (warp < S3::ITEMS)
-      flush_item<S3::CNT>(G, a.po[4], a.po[5], K3, 64, warp / S3::GROUPS, (warp % S3::GROUPS) * S3::CNT, wg3, wb3, (warp % S3::GROUPS) == 0, g8, t4);
+      flush_item<S3::CNT>(G, a.po[4], a.po[5], 15, 64, warp / S3::GROUPS, (warp % S3::GROUPS) * S3::CNT, wg3, wb3, (warp % S3::GROUPS) == 0, g8, t4, K3, V);
+    if (warp < S3::ITEMS && (warp % S3::GROUPS) == 0) {        // the strip owners hold dW3[:, views]
+      const int strip = warp / S3::GROUPS;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int v = t4 + 4 * k;
+        if (v < V) {
+          if (w3v[k][0] != 0.f) red_add(G + a.po[4] + (strip * 16 + g8) * K3 + v, w3v[k][0]);
+          if (w3v[k][1] != 0.f) red_add(G + a.po[4] + (strip * 16 + g8 + 8) * K3 + v, w3v[k][1]);
+        }
+      }
+    }
     if (warp < S4::ITEMS)
       flush_item<S4::CNT>(G, a.po[6], a.po[7], 64, 64, warp / S4::GROUPS, (warp % S4::GROUPS) * S4::CNT, wg4, wb4, (warp % S4::GROUPS) == 0, g8, t4);
     if (warp < S5::ITEMS)
@@ -849,8 +768,9 @@ static int launch_tc(const StepArgs& a, int blocks, cudaStream_t st) {
   const size_t smem = step_tc_smem(KE);
   // function attributes are per device: set on every launch (a cheap host-side call) rather than once per process
   cudaFuncSetAttribute(tc::step_tc_kernel<KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  static_assert((size_t)(64 * KE * 2 + 16 * 64 * 2 + 64 * KC * 2 + 64 * 64 * 2 + 16 * 64 * 2 + 216 * 4 + 6 * 128 + 16) <= kWPackBytes, "wpack too small");
-  tc::pack_mlp_kernel<KE><<<(tc::make_plan(KE).x0 / 4 + 255) / 256, 256, 0, st>>>(a);
+  const img::ImagePlan ip = img::make_image_plan(KE);
+  if ((size_t)ip.bytes + 16 > kWPackBytes) { set_error("nof_step_fused(tc): operand image too large"); return NOF_E_INVALID; }
+  img::pack_image_kernel<KE><<<(ip.bytes / 4 + 255) / 256, 256, 0, st>>>(a);
   tc::step_tc_kernel<KE><<<blocks, tc::NT, smem, st>>>(a);
   return check_launch("step_tc_kernel");
 }

@@ -16,8 +16,7 @@
 // feature) are identical for all samples of a ray, so their product with W3 is computed ONCE per ray and enters layer 3 as a per-ray
 // bias; the tile GEMM only carries the 15 geometry features (K = 16), and the matching gradients (dW3[:, views], d views) come from
 // the per-ray column sums of dY3 that the weight-gradient warps produce anyway for the bias gradient.
-#include "nof_step_common.cuh"
-#include "nof_tc_prims.cuh"
+#include "nof_mlp_image.cuh"
 
 namespace nof {
 namespace ws {
@@ -26,8 +25,8 @@ using namespace prim;
 constexpr int PT = 128;                       // points per tile = UMMA M
 constexpr int NS = 3;                         // tile slots in flight
 constexpr int NRAY = 12;                      // ray-state ring: 3 tiles x 4 rays
-constexpr int KG = 16;                        // colour-net GEMM input: geo(15) + pad
-constexpr int VPAD = 18;                      // row length of the fp16 W3[:, views] block (V <= 17)
+using img::KG;
+using img::VPAD;
 constexpr int DES = PT + PT / 8;              // padded point stride of the transposed arrays (index pt + pt/8)
 __device__ __forceinline__ int des_idx(int pt) { return pt + (pt >> 3); }
 
@@ -80,15 +79,10 @@ __host__ __device__ inline Plan make_plan(int KE) {
   Plan s;
   int o = 0;
   auto take = [&](int bytes) { int r = o; o += (bytes + 127) / 128 * 128; return r; };
-  s.w1 = take(64 * KE * 2);
-  s.w2 = take(16 * 64 * 2);
-  s.w3g = take(64 * KG * 2);
-  s.w4 = take(64 * 64 * 2);
-  s.w5 = take(16 * 64 * 2);
-  s.bias = take(280 * 4);                     // b1 64 | b2 16 | b3 64 | b4 64 | b5 8 | 64 zeros (the 'no per-ray bias' vector)
-  s.w3v = take(64 * VPAD * 2);
-  s.lv = take((int)sizeof(LevelS));
-  s.img_bytes = o;
+  const img::ImagePlan ip = img::make_image_plan(KE);
+  s.w1 = ip.w1; s.w2 = ip.w2; s.w3g = ip.w3g; s.w4 = ip.w4; s.w5 = ip.w5; s.bias = ip.bias; s.w3v = ip.w3v; s.lv = ip.lv;
+  s.img_bytes = ip.bytes;
+  o = ip.bytes;
   s.slot0 = o;
   int q = 0;
   auto stake = [&](int bytes) { int r = q; q += (bytes + 127) / 128 * 128; return r; };
@@ -127,61 +121,6 @@ struct PhaseWaiter {
     return true;
   }
 };
-
-// ------------------------------------------------------------------------------------------------ operand image
-// fp32 packed parameters -> [W1 | W2 | W3[:, geo] | W4 | W5 (core-matrix fp16, zero padded) | biases (fp32, fp16-rounded) |
-// W3[:, views] fp16 row-major [64][VPAD] | level geometry]. One small kernel per step; also zeroes the per-step outputs and the tile ticket.
-template <int KE>
-__global__ void __launch_bounds__(256) pack_ws_kernel(const StepArgs a) {
-  const Plan sp = make_plan(KE);
-  unsigned char* out = static_cast<unsigned char*>(a.wpack);
-  const int gid = blockIdx.x * 256 + threadIdx.x;
-  if (gid == 0) *reinterpret_cast<int*>(out + kWPackBytes - 16) = 0;                 // tile ticket of the step kernel
-  if (gid < 8) a.p.losses[gid] = 0.f;                                                // per-step results start from zero
-  if (a.p.grad_tf) for (int i = gid; i < a.p.F * 12; i += gridDim.x * 256) a.p.grad_tf[i] = 0.f;
-  const float* P = a.p.mlp;
-  const int V = a.V, K3 = V + 15;
-  const int o = gid * 4;                                          // one 32-bit word of the image per thread
-  if (o < sp.bias) {
-    int base, rows, kreal, kpad, po, kofs = 0, ld;
-    if (o >= sp.w5) { base = sp.w5; rows = 3; kreal = 64; kpad = 64; po = a.po[8]; ld = 64; }
-    else if (o >= sp.w4) { base = sp.w4; rows = 64; kreal = 64; kpad = 64; po = a.po[6]; ld = 64; }
-    else if (o >= sp.w3g) { base = sp.w3g; rows = 64; kreal = 15; kpad = KG; po = a.po[4]; kofs = V; ld = K3; }
-    else if (o >= sp.w2) { base = sp.w2; rows = 16; kreal = 64; kpad = 64; po = a.po[2]; ld = 64; }
-    else { base = sp.w1; rows = 64; kreal = a.E; kpad = KE; po = a.po[0]; ld = a.E; }
-    const int rel = o - base, rg = rel / (kpad * 16), rem = rel % (kpad * 16);
-    const int n = rg * 8 + (rem % 128) / 16, k = (rem / 128) * 8 + (rem % 16) / 2;          // inverse of cm_off
-    const float v0 = (n < rows && k < kreal) ? P[po + n * ld + kofs + k] : 0.f;
-    const float v1 = (n < rows && k + 1 < kreal) ? P[po + n * ld + kofs + k + 1] : 0.f;
-    *reinterpret_cast<uint32_t*>(out + o) = pack_h2(v0, v1);
-  } else if (o < sp.w3v) {
-    const int j = (o - sp.bias) / 4;
-    float v = 0.f;
-    if (j < 64) v = P[a.po[1] + j];
-    else if (j < 80) v = P[a.po[3] + j - 64];
-    else if (j < 144) v = P[a.po[5] + j - 80];
-    else if (j < 208) v = P[a.po[7] + j - 144];
-    else if (j < 211) v = P[a.po[9] + j - 208];
-    *reinterpret_cast<float*>(out + o) = __half2float(__float2half_rn(v));
-  } else if (o < sp.lv) {
-    const int e = (o - sp.w3v) / 2, n = e / VPAD, k = e % VPAD;
-    const float v0 = (n < 64 && k < V) ? P[a.po[4] + n * K3 + k] : 0.f;
-    const float v1 = (n < 64 && k + 1 < V) ? P[a.po[4] + n * K3 + k + 1] : 0.f;
-    *reinterpret_cast<uint32_t*>(out + o) = pack_h2(v0, v1);
-  } else if (o < sp.img_bytes) {
-    const int l = (o - sp.lv) / 4;                               // thread l (< MAX_L) fills column l of every LevelS array
-    if (l < MAX_L) {
-      LevelS* lv = reinterpret_cast<LevelS*>(out + sp.lv);
-      if (l < a.p.L) {
-        LevelGeom g = level_geom3(l, a.p.S_log2, a.p.H, a.p.offsets);
-        lv->scale[l] = g.scale; lv->res1[l] = g.resolution + 1u; lv->hsize[l] = g.hashmap_size; lv->off[l] = g.offset; lv->dense[l] = g.dense;
-        lv->hmask[l] = (g.hashmap_size & (g.hashmap_size - 1)) == 0 ? g.hashmap_size - 1 : 0u;
-      } else {
-        lv->scale[l] = 0.f; lv->res1[l] = 1u; lv->hsize[l] = 1u; lv->off[l] = 0u; lv->dense[l] = 1u; lv->hmask[l] = 0u;
-      }
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ small helpers
 template <typename R>
@@ -1099,7 +1038,7 @@ static int launch_ws(const StepArgs& a, int blocks, cudaStream_t st) {
   cudaFuncSetAttribute(ws::step_ws_kernel<KE, POSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per-device attribute
   const ws::Plan sp = ws::make_plan(KE);
   if ((size_t)sp.img_bytes + 16 > kWPackBytes) { set_error("nof_step_fused(ws): operand image too large"); return NOF_E_INVALID; }
-  ws::pack_ws_kernel<KE><<<(sp.img_bytes / 4 + 255) / 256, 256, 0, st>>>(a);
+  img::pack_image_kernel<KE><<<(sp.img_bytes / 4 + 255) / 256, 256, 0, st>>>(a);
   ws::step_ws_kernel<KE, POSE><<<blocks, ws::NT, smem, st>>>(a);
   return check_launch("step_ws_kernel");
 }
