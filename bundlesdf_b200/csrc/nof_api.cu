@@ -70,9 +70,6 @@ static void mlp_offsets(int E, int V, int32_t o[10], size_t* total) {
   if (total) *total = (size_t)acc;
 }
 
-template <bool HALF, bool COUNT>
-__global__ void query_sdf_kernel(const StepArgs a, const float* __restrict__ xin, float* __restrict__ sdf, int64_t P, int* __restrict__ count);
-
 struct Tiling { int NW, Sp, R, n_groups, blocks; };
 
 // AMP: one CTA = R whole rays, thread = sample; supported CTA sizes 128/192/256/320 threads.
@@ -195,21 +192,16 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
   a.inv_N3 = 1.0f / (3.0f * (float)p->N);
   a.inv_NS = 1.0f / ((float)p->N * (float)p->S);
   a.inv_NS3 = a.inv_NS / 3.0f;
+  a.count_only = 0;
   a.wpack = p->workspace;                                   // [0, kWPackBytes): packed fp16 MLP operands (tcgen05 path)
   a.jws = static_cast<char*>(p->workspace) + kWPackBytes;   // then the per-CTA Jacobian scratch
   Tiling t;
   const bool eik = p->eikonal_weight > 0.f;
   NOF_REQUIRE(!eik || (p->amp && p->S <= 256), "nof_step_fused: eikonal_weight > 0 is built for amp: true and S <= 256 (S=%d amp=%d)", p->S, p->amp);
   if (eik) {
-    // the term is a mean over the selected samples of the WHOLE batch: count them first (SDF-only forward of all N*S samples)
+    // the term is a mean over the selected samples of the WHOLE batch: they are counted first, by a forward-only pass of the tile kernel
     int* cnt = reinterpret_cast<int*>(static_cast<char*>(a.wpack) + kWPackBytes - 32);
     cudaMemsetAsync(cnt, 0, sizeof(int), as_stream(stream));
-    const int64_t P = (int64_t)p->N * p->S;
-    const size_t smem_q = (size_t)(64 * a.E + 128) * 4;
-    const int qblocks = (int)std::min<int64_t>((P + 255) / 256, (int64_t)sms * 8);
-    query_sdf_kernel<true, true><<<qblocks, 256, smem_q, as_stream(stream)>>>(a, nullptr, nullptr, P, cnt);
-    rc = check_launch("eik_count (query_sdf_kernel)");
-    if (rc) return rc;
   }
   if (p->amp && !eik && amp_impl_for(p->S) == 2) {
     int Sp, R;
@@ -229,6 +221,12 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
     NOF_REQUIRE(step_amp_smem(t.NW * 32, a.KE, eik) <= (size_t)smem_max, "nof_step_fused(amp): needs %zu B shared memory, device allows %d",
                 step_amp_smem(t.NW * 32, a.KE, eik), smem_max);
     zero_step_outputs(p, as_stream(stream));
+    if (eik) {                                              // counting pass: same kernel, forward up to the sdf only
+      a.count_only = 1;
+      rc = step_amp_dispatch(a, t.NW, t.blocks, as_stream(stream));
+      if (rc) return rc;
+      a.count_only = 0;
+    }
     return step_amp_dispatch(a, t.NW, t.blocks, as_stream(stream));
   }
   NOF_REQUIRE(f32_tiling(p, sms, &t), "nof_step_fused(fp32): S=%d not supported (R*ceil32(S) must be <= 1024 with R<=4)", p->S);
@@ -243,10 +241,8 @@ extern "C" int nof_step_fused(const NofStep* p, nof_stream_t stream) {
 // SDF-only query (mesh extraction): encode + sigma_net, thread = point, weights broadcast from shared memory.
 // ------------------------------------------------------------------------------------------------
 namespace nof {
-// COUNT: instead of writing the sdf of given points, visit the N*S samples of the batch (rays, tf, z_vals) and count those the eikonal
-// term averages over: sdf < 1, out-of-bounds samples included with sdf = 0 (oracle.eikonal_loss / nerf_runner.py:737 `normals[sdf<1]`).
-template <bool HALF, bool COUNT>
-__global__ void __launch_bounds__(256) query_sdf_kernel(const StepArgs a, const float* __restrict__ xin, float* __restrict__ sdf, int64_t P, int* __restrict__ count) {
+template <bool HALF>
+__global__ void __launch_bounds__(256) query_sdf_kernel(const StepArgs a, const float* __restrict__ xin, float* __restrict__ sdf, int64_t P) {
   extern __shared__ __align__(16) float sq[];
   __shared__ LevelS lv;
   const int E = a.E;
@@ -264,28 +260,10 @@ __global__ void __launch_bounds__(256) query_sdf_kernel(const StepArgs a, const 
   if (HALF) b2 = __half2float(__float2half_rn(b2));
   init_levels(lv, a);
   __syncthreads();
-  int n_sel = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
     float u[3];
-    if (COUNT) {
-      const int ray = (int)(i / a.p.S);
-      const float* row = a.p.rays + (size_t)ray * a.p.ray_dim;
-      const int frame = min(max((int)row[8], 0), a.p.F - 1);
-      const float* T = a.p.tf + (size_t)frame * 12;
-      const float z = a.p.z_vals[i];
-      const float pc[3] = {row[0] * z, row[1] * z, row[2] * z};
-      bool valid = true;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {                             // same arithmetic as world_point of the step kernels
-        const float x = fmaf(T[d * 4 + 2], pc[2], fmaf(T[d * 4 + 1], pc[1], T[d * 4 + 0] * pc[0])) + T[d * 4 + 3];
-        valid = valid && fabsf(x) <= 1.f;
-        u[d] = (x + 1.0f) * 0.5f;
-      }
-      if (!valid) { ++n_sel; continue; }
-    } else {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) u[d] = (fminf(fmaxf(xin[i * 3 + d], -1.f), 1.f) + 1.f) * 0.5f;   // nerf_runner.py:1314, grid.py:160
-    }
+    for (int d = 0; d < 3; ++d) u[d] = (fminf(fmaxf(xin[i * 3 + d], -1.f), 1.f) + 1.f) * 0.5f;   // nerf_runner.py:1314, grid.py:160
     float enc[32];
 #pragma unroll
     for (int l = 0; l < MAX_L; ++l) {
@@ -304,13 +282,7 @@ __global__ void __launch_bounds__(256) query_sdf_kernel(const StepArgs a, const 
       if (HALF) acc = __half2float(__float2half_rn(acc));
       out = fmaf(acc, sW2[o], out);
     }
-    const float res = HALF ? __half2float(__float2half_rn(out)) : out;
-    if (COUNT) n_sel += res < 1.f ? 1 : 0;
-    else sdf[i] = res;
-  }
-  if (COUNT) {
-    for (int o = 16; o > 0; o >>= 1) n_sel += __shfl_xor_sync(0xffffffffu, n_sel, o);
-    if ((threadIdx.x & 31) == 0 && n_sel) atomicAdd(count, n_sel);
+    sdf[i] = HALF ? __half2float(__float2half_rn(out)) : out;
   }
 }
 }  // namespace nof
@@ -327,12 +299,13 @@ extern "C" int nof_query_sdf(const NofStep* model, const float* x, float* sdf, i
   a.KE = (a.E + 15) / 16 * 16;
   mlp_offsets(a.E, a.V, a.po, nullptr);
   a.R = a.Sp = a.n_groups = 0;
+  a.count_only = 0;
   a.inv_N3 = a.inv_NS = a.inv_NS3 = 0.f;
   int sms = 148;
   nof_device_info(&sms, nullptr);
   const size_t smem = (size_t)(64 * a.E + 128) * 4;
   const int blocks = (int)std::min<int64_t>((P + 255) / 256, (int64_t)sms * 8);
-  if (model->amp) query_sdf_kernel<true, false><<<blocks, 256, smem, as_stream(stream)>>>(a, x, sdf, P, nullptr);
-  else query_sdf_kernel<false, false><<<blocks, 256, smem, as_stream(stream)>>>(a, x, sdf, P, nullptr);
+  if (model->amp) query_sdf_kernel<true><<<blocks, 256, smem, as_stream(stream)>>>(a, x, sdf, P);
+  else query_sdf_kernel<false><<<blocks, 256, smem, as_stream(stream)>>>(a, x, sdf, P);
   return check_launch("query_sdf_kernel");
 }

@@ -75,6 +75,7 @@ __global__ void interval_walk_kernel(const float* __restrict__ z_in_out, const f
 
 // ------------------------------------------------------------------------------------------------
 constexpr int MARCH_WARPS = 8;
+constexpr int WALK_FLOATS = 3 * 64 + 8;     // per warp: event times of the three axes (up to 64 crossings each, level <= 6) + 8 words of keep bits
 
 // torch.linspace(0,1,S) as its CUDA kernel evaluates it (step=(end-start)/(steps-1); lower half start+step*i, upper half
 // end-step*(steps-i-1), each contracted to one FMA); the division is hoisted out of the per-sample code.
@@ -99,12 +100,10 @@ __device__ __forceinline__ float strat_one(const Lin& L, int i, float nearv, flo
   return z;
 }
 
-// One warp per ray. The voxel DDA is a sequential walk on lane 0 (sharing one instruction stream between 8 rays on 8 lanes of
-// one warp was tried: the walk's dependent chain, not issue slots, is what the kernel waits for, 19.7 -> 24.8 us), so the step is
-// kept short: the exit time of each axis is cached and recomputed only for the axis that moved (a pure function of ix[a], hence
-// bit-identical to recomputing all three), and the reference's `(double)|dt| < 1e-4` is the float test `|dt| <= 1e-4f` (the
-// float nearest to 1e-4 lies below it, the next one above). Samples: all 32 lanes, a lane owns 4 consecutive samples (one
-// Philox call, one 16-byte store).
+// One warp per ray. Phase 1 (the walk through the occupancy grid) is warp-parallel over the plane-crossing events (see the comment in the
+// kernel; round 1 walked the cells sequentially on lane 0: 3.4 k warp instructions per ray, half of them that dependent chain). The
+// reference's `(double)|dt| < 1e-4` is the float test `|dt| <= 1e-4f` (the float nearest to 1e-4 lies below it, the next one above).
+// Phase 2 (samples): all 32 lanes, a lane owns 4 consecutive samples (one Philox call, one 16-byte store).
 __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg cfg, const float* __restrict__ rays,
                                                                      const float* __restrict__ tf,
                                                                      const uint32_t* __restrict__ occ_bits,
@@ -120,6 +119,7 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg
   float* s_io_t = reinterpret_cast<float*>(smem_u32 + occ_words);       // [MARCH_WARPS][I][2] travel-time intervals per ray
   float* s_io_z = s_io_t + (size_t)MARCH_WARPS * I * 2;                 // [MARCH_WARPS][I][2] z intervals (scaled, clipped)
   int* s_count = reinterpret_cast<int*>(s_io_z + (size_t)MARCH_WARPS * I * 2);   // [MARCH_WARPS] intervals, [MARCH_WARPS] overflow
+  float* s_walk = reinterpret_cast<float*>(s_count + 2 * MARCH_WARPS);            // [MARCH_WARPS][WALK_FLOATS] event times + keep bits
   for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s_occ[i] = occ_bits[i];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,8 +130,13 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg
 
   __syncthreads();                                     // bitmask staged
   for (int r = blockIdx.x * MARCH_WARPS + warp; r < cfg.N; r += gridDim.x * MARCH_WARPS) {
-    // ================= phase 1: DDA (replaces kaolin unbatched_raytrace; packing rule of common.cu:137-148 applied on the fly)
-    if (lane == 0) {
+    // ================= phase 1: the ray's walk through the occupancy grid (replaces kaolin unbatched_raytrace; packing rule of
+    // common.cu:137-148), WARP-PARALLEL. The exit time of a cell through the k-th plane of axis a is a closed form of k and non-decreasing
+    // in k, so the sequential voxel walk is the merge of three sorted lists ordered by (T, axis) — `t < t_out` with the axes tried in order
+    // 0,1,2 is exactly that tie rule (oracle.ray_trace_intervals_merge, bit-identical to the sequential oracle.ray_trace_intervals).
+    // Lane = event: its rank m in the merged order comes from two binary searches, step m's cell from the per-axis event counts before
+    // it, t_in from the latest of the three predecessors; only the packing rule needs two warp reductions and a bitmask prefix count.
+    {
       const float* row = rays + (size_t)r * cfg.ray_dim;
       const float dx = row[0], dy = row[1], dz = row[2];
       const float* T = tf + (size_t)((int)row[8]) * 12;
@@ -146,9 +151,10 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg
         inv[a] = __fdiv_rn(1.0f, d[a]);
       }
       float* io_t = s_io_t + (size_t)warp * I * 2;
-      int count = 0;
-      bool overflow = false;
-      float t0 = 0.f, t1 = __int_as_float(0x7f800000);
+      float* sT = s_walk + (size_t)warp * WALK_FLOATS;          // [3][64] event times, then 8 words of keep bits
+      uint32_t* sKeep = reinterpret_cast<uint32_t*>(sT + 3 * 64);
+      const float INF = __int_as_float(0x7f800000);
+      float t0 = 0.f, t1 = INF;
       bool hit = true;
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -161,56 +167,112 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg
           t1 = fminf(t1, fmaxf(ta, tb));
         }
       }
-      if (hit && t0 < t1) {
+      int count = 0;
+      bool overflow = false;
+      if (lane < 8) sKeep[lane] = 0u;
+      if (hit && t0 < t1) {                                     // warp-uniform (every lane computed the same ray)
         const float cell = __fdiv_rn(2.0f, (float)n);
-        int ix[3], step[3];
-        float tnext[3];                                 // exit time through the next plane of each axis: a pure function of ix[a]
-        auto plane_t = [&](int a) {
-          const float plane = __fsub_rn(__fmul_rn((float)(ix[a] + (step[a] > 0 ? 1 : 0)), cell), 1.0f);
-          return __fmul_rn(__fsub_rn(plane, o[a]), inv[a]);
-        };
+        int ix0[3], step[3], K[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const float p = __fadd_rn(o[a], __fmul_rn(t0, d[a]));
           const int c = (int)floorf(__fdiv_rn(__fadd_rn(p, 1.0f), cell));
-          ix[a] = min(max(c, 0), n - 1);
+          ix0[a] = min(max(c, 0), n - 1);
           step[a] = d[a] > 0.f ? 1 : (d[a] < 0.f ? -1 : 0);
-          tnext[a] = step[a] != 0 ? plane_t(a) : __int_as_float(0x7f800000);
+          K[a] = step[a] > 0 ? n - ix0[a] : (step[a] < 0 ? ix0[a] + 1 : 0);     // crossings until the walk leaves the grid on this axis
         }
-        float t_in = t0;
-        bool stopped = false;                           // the packing rule's `break` (t_in==0 || t_out==0)
-        for (int guard = 0; guard < 3 * n + 3; ++guard) {
-          float t_out = __int_as_float(0x7f800000);
-          int ax = -1;
+        // event times T_a[k] (padded with +inf): the walk's plane_t of cell ix0_a + k step_a
+        for (int e = lane; e < 3 * 64; e += 32) {
+          const int a = e >> 6, k = e & 63;
+          float t = INF;
+          if (k < K[a]) {
+            const int ixa = ix0[a] + k * step[a];
+            const float plane = __fsub_rn(__fmul_rn((float)(ixa + (step[a] > 0 ? 1 : 0)), cell), 1.0f);
+            t = __fmul_rn(__fsub_rn(plane, o[a]), inv[a]);
+          }
+          sT[e] = t;
+        }
+        __syncwarp();
+        // number of events of list `b` (K_b long) ordered before time t: strictly smaller, or also equal when `incl`
+        auto count_before = [&](int bb, float t, bool incl) {
+          const float* L = sT + bb * 64;
+          int lo = 0, hi = K[bb];
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const float v = L[mid];
+            if (v < t || (incl && v == t)) lo = mid + 1; else hi = mid;
+          }
+          return lo;
+        };
+        const int n_ev = 3 * n;                                 // event slots: axis a = e / n, crossing k = e % n
+        int m_end = 3 * n + 2, first_zero = 0x7fffffff;
+        // pass 1: every lane evaluates its events (at most ceil(3n/32) of them); keeps them in registers for pass 2
+        constexpr int MAX_EV = 6;                               // 3 * 64 / 32
+        int ev_m[MAX_EV];
+        float ev_in[MAX_EV], ev_out[MAX_EV];
+        bool ev_occ[MAX_EV];
 #pragma unroll
-          for (int a = 0; a < 3; ++a)
-            if (step[a] != 0 && tnext[a] < t_out) { t_out = tnext[a]; ax = a; }
-          if (ax < 0) break;
-          t_out = fminf(t_out, t1);
-          const int cid = (ix[0] * n + ix[1]) * n + ix[2];
-          if (!stopped && ((s_occ[cid >> 5] >> (cid & 31)) & 1u)) {
-            if (t_in == 0.f || t_out == 0.f) {
-              stopped = true;
-            } else if (!(t_in > t_out) && !(fabsf(__fsub_rn(t_out, t_in)) <= 1e-4f)) {
-              if (count < I) {
-                io_t[2 * count] = t_in;
-                io_t[2 * count + 1] = t_out;
-                ++count;
-              } else {
-                overflow = true;
-              }
+        for (int j = 0; j < MAX_EV; ++j) {
+          ev_m[j] = -1; ev_in[j] = 0.f; ev_out[j] = 0.f; ev_occ[j] = false;
+          const int e = lane + 32 * j;
+          if (e < n_ev) {
+            const int a = e / n, k = e - a * n;
+            if (k < K[a]) {
+              const int b1 = a == 0 ? 1 : 0, b2 = a == 2 ? 1 : 2;            // the other two axes, b1 < b2
+              const float t = sT[a * 64 + k];
+              const int c1 = count_before(b1, t, b1 < a), c2 = count_before(b2, t, b2 < a);
+              const int m = k + c1 + c2;
+              float tprev = -INF;
+              if (k > 0) tprev = sT[a * 64 + k - 1];
+              if (c1 > 0) tprev = fmaxf(tprev, sT[b1 * 64 + c1 - 1]);
+              if (c2 > 0) tprev = fmaxf(tprev, sT[b2 * 64 + c2 - 1]);
+              const float t_out = fminf(t, t1);
+              const float t_in = m == 0 ? t0 : fminf(tprev, t1);
+              int cix[3];
+              cix[a] = ix0[a] + k * step[a];
+              cix[b1] = ix0[b1] + c1 * step[b1];
+              cix[b2] = ix0[b2] + c2 * step[b2];
+              const int cid = (min(max(cix[0], 0), n - 1) * n + min(max(cix[1], 0), n - 1)) * n + min(max(cix[2], 0), n - 1);
+              ev_m[j] = m; ev_in[j] = t_in; ev_out[j] = t_out;
+              ev_occ[j] = (s_occ[cid >> 5] >> (cid & 31)) & 1u;
+              if (k == K[a] - 1 || t_out >= t1) m_end = min(m_end, m);        // the walk ends with the step that leaves the grid / reaches t1
             }
           }
-          if (ax == 0) { ix[0] += step[0]; tnext[0] = plane_t(0); }
-          else if (ax == 1) { ix[1] += step[1]; tnext[1] = plane_t(1); }
-          else { ix[2] += step[2]; tnext[2] = plane_t(2); }
-          const int moved = ax == 0 ? ix[0] : (ax == 1 ? ix[1] : ix[2]);
-          if (moved < 0 || moved >= n || t_out >= t1) break;
-          t_in = t_out;
         }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m_end = min(m_end, __shfl_xor_sync(0xffffffffu, m_end, off));
+#pragma unroll
+        for (int j = 0; j < MAX_EV; ++j) {
+          ev_occ[j] = ev_occ[j] && ev_m[j] >= 0 && ev_m[j] <= m_end;
+          if (ev_occ[j] && (ev_in[j] == 0.f || ev_out[j] == 0.f)) first_zero = min(first_zero, ev_m[j]);   // the packing rule's `break`
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) first_zero = min(first_zero, __shfl_xor_sync(0xffffffffu, first_zero, off));
+        // pass 2: keep flags as a bitmask over the step index, then ordered compaction by prefix popcount
+#pragma unroll
+        for (int j = 0; j < MAX_EV; ++j) {
+          ev_occ[j] = ev_occ[j] && ev_m[j] < first_zero && !(ev_in[j] > ev_out[j]) && !(fabsf(__fsub_rn(ev_out[j], ev_in[j])) <= 1e-4f);
+          if (ev_occ[j]) atomicOr(&sKeep[ev_m[j] >> 5], 1u << (ev_m[j] & 31));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < MAX_EV; ++j) {
+          if (ev_occ[j]) {
+            const int m = ev_m[j];
+            int pos = __popc(sKeep[m >> 5] & ((1u << (m & 31)) - 1u));
+            for (int wq = 0; wq < (m >> 5); ++wq) pos += __popc(sKeep[wq]);
+            if (pos < I) { io_t[2 * pos] = ev_in[j]; io_t[2 * pos + 1] = ev_out[j]; }
+          }
+        }
+        int total = 0;
+        for (int wq = 0; wq < 8; ++wq) total += __popc(sKeep[wq]);
+        overflow = total > I;
+        count = min(total, I);
       }
-      s_count[warp] = count;
-      s_count[MARCH_WARPS + warp] = overflow ? 1 : 0;
+      if (lane == 0) {
+        s_count[warp] = count;
+        s_count[MARCH_WARPS + warp] = overflow ? 1 : 0;
+      }
     }
     __syncwarp();
     // ================= phase 2: samples
@@ -354,7 +416,8 @@ extern "C" int nof_ray_march(const NofMarchCfg* cfg, const float* rays, const fl
   NOF_REQUIRE(cfg->S_occ >= 1 && cfg->S_depth >= 0, "nof_ray_march: bad sample counts");
   if (cfg->N == 0) return NOF_OK;
   const int n = 1 << cfg->level;
-  const size_t smem = (size_t)((n * n * n + 31) / 32) * 4 + (size_t)MARCH_WARPS * cfg->I_max * 4 * sizeof(float) + 2 * MARCH_WARPS * sizeof(int);
+  const size_t smem = (size_t)((n * n * n + 31) / 32) * 4 + (size_t)MARCH_WARPS * cfg->I_max * 4 * sizeof(float) + 2 * MARCH_WARPS * sizeof(int) +
+                      (size_t)MARCH_WARPS * WALK_FLOATS * sizeof(float);
   if (smem > 48 * 1024)      // per-device attribute: set whenever it is needed, not once per process
     cudaFuncSetAttribute(ray_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   NOF_REQUIRE(smem <= 100 * 1024, "nof_ray_march: shared memory %zu too large", smem);

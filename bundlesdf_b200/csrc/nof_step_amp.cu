@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128 && !EIK) ? 2 : 1) step_amp_
   // eikonal term: its weight over the number of selected samples (counted by eik_count_kernel before this launch),
   // times the loss scale; accumulators of d L_eik / d W2[0,:] (lanes with g8 == 0 own columns nt*8 + 2*t4, +1)
   float eik_loss = 0.f, w2e[8][2];
+  int n_sel = 0;
   __half* Qh = reinterpret_cast<__half*>(smem + sp.qh);
   float* nbuf = reinterpret_cast<float*>(smem + sp.nbuf);
   const float eik_c = EIK ? a.p.eikonal_weight / fmaxf((float)*reinterpret_cast<const int*>(static_cast<const char*>(a.wpack) + kWPackBytes - 32), 1.f) : 0.f;
@@ -543,7 +544,15 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128 && !EIK) ? 2 : 1) step_amp_
           }
         }
       __syncwarp();
-      if constexpr (EIK) eikonal_block();
+      if constexpr (EIK) {
+        if (a.count_only) {                                 // counting pass: the sdf of every sample is all it needs (same arithmetic as the real pass)
+          __syncthreads();
+          if (owner && active && (!valid || sOut[pt * 4 + 3] < 1.f)) n_sel += 1;
+          __syncthreads();                                  // sOut / ray state free for the next tile
+          continue;
+        }
+        eikonal_block();
+      }
       // ---- L3: (V+15 padded 32) -> 64, ReLU
       init_bias<8>(acc, sB + 80, t4);
       warp_fwd<KC, 64>(XC + (size_t)row0 * LD32, LD32, sW3, LD32, acc, lane);
@@ -794,6 +803,11 @@ __global__ void __launch_bounds__(2 * PT, (PT <= 128 && !EIK) ? 2 : 1) step_amp_
   }
   {
     if constexpr (EIK) {
+      if (a.count_only) {
+        for (int o = 16; o > 0; o >>= 1) n_sel += __shfl_xor_sync(0xffffffffu, n_sel, o);
+        if (lane == 0 && n_sel) atomicAdd(reinterpret_cast<int*>(static_cast<char*>(a.wpack) + kWPackBytes - 32), n_sel);
+        return;
+      }
       if (g8 == 0) {
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {

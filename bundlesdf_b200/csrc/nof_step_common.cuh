@@ -24,6 +24,7 @@ struct StepArgs {
   float inv_N3, inv_NS, inv_NS3;
   void* jws;                    // workspace: per-CTA Jacobian scratch
   void* wpack;                  // workspace: fp16 MLP operands pre-packed for the tcgen05 kernel (kWPackBytes)
+  int count_only;               // eikonal: first pass of the tile kernel — forward up to the sdf, count the samples with sdf < 1, nothing else
 };
 constexpr size_t kWPackBytes = 32 * 1024;
 
