@@ -123,7 +123,11 @@ template <bool HALF> struct TableT;
 template <> struct TableT<true> {
   using vec = __half2;
   static __device__ __forceinline__ float2 load(const void* table, uint32_t entry) {
+#ifdef NOF_EXP_STAGE_L0   // ablation only (profiles/README.md): `table` may point into shared memory, so no ld.global.nc
+    const __half2 h = *(reinterpret_cast<const __half2*>(table) + entry);
+#else
     const __half2 h = __ldg(reinterpret_cast<const __half2*>(table) + entry);
+#endif
     return __half22float2(h);
   }
 };

@@ -42,7 +42,7 @@ struct RayT : RayS {                          // + the per-ray share of the colo
 };
 
 struct Plan {
-  int w1, w2, w3, w4, w5, bias, w3v, lv, img_bytes, x0, x1, xc, x3, x4, d_o, out, zs, rays, bar, tmem, total;
+  int w1, w2, w3, w4, w5, bias, w3v, lv, img_bytes, x0, x1, xc, x3, x4, d_o, out, zs, rays, bar, tmem, l0, total;
 };
 __host__ __device__ inline Plan make_plan(int KE) {
   Plan s;
@@ -61,6 +61,11 @@ __host__ __device__ inline Plan make_plan(int KE) {
   s.rays = take(MAX_R * (int)sizeof(RayT));
   s.bar = take(64);                          // [0] TMA staging barrier, [1] MMA completion barrier
   s.tmem = take(16);
+#ifdef NOF_EXP_STAGE_L0   // ablation: level 0 of the fp16 table (17^3 entries) staged in shared memory by TMA
+  s.l0 = take(4920 * 4);
+#else
+  s.l0 = o;
+#endif
   s.total = o;
   return s;
 }
@@ -222,10 +227,20 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   const uint32_t tmem = *s_tmem;
   // MLP operands: already fp16, core-matrix ordered and zero-padded (pack_mlp_kernel) — one bulk copy, no conversion
   const uint32_t pack_bytes = (uint32_t)sp.img_bytes;
+#ifdef NOF_EXP_STAGE_L0
+  const uint32_t l0_bytes = (uint32_t)(a.p.offsets[1] - a.p.offsets[0]) * 4u;          // level 0 of the table, 16-byte multiple (grid.py pads to 8 entries)
+  const unsigned char* table0 = smem + sp.l0 - (size_t)a.p.offsets[0] * 4;              // so that table0[off0 + idx] is the staged copy
+  if (tid == 0) {
+    mbar_expect_tx(bar_tma, pack_bytes + l0_bytes);
+    tma_bulk_g2s(smem + sp.w1, a.wpack, pack_bytes, bar_tma);
+    tma_bulk_g2s(smem + sp.l0, static_cast<const unsigned char*>(a.p.table_f16) + (size_t)a.p.offsets[0] * 4, l0_bytes, bar_tma);
+  }
+#else
   if (tid == 0) {
     mbar_expect_tx(bar_tma, pack_bytes);
     tma_bulk_g2s(smem + sp.w1, a.wpack, pack_bytes, bar_tma);
   }
+#endif
   bool tc_ok = mbar_wait_inl(bar_tma, 0);
   fence_async_smem();
   __syncthreads();
@@ -320,7 +335,11 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
       for (int l = l_beg; l < l_end; ++l) {
         float enc[2], J[3][2];
         if (a.p.need_pose_grad) {
+#ifdef NOF_EXP_STAGE_L0
+          gather_level<true, true>(l == 0 ? (const void*)table0 : a.p.table_f16, lv, l, u, enc, J);
+#else
           gather_level<true, true>(a.p.table_f16, lv, l, u, enc, J);
+#endif
 #pragma unroll
           for (int d = 0; d < 3; ++d) Jslot[(size_t)(l * 3 + d) * PT + pt] = __floats2half2_rn(J[d][0], J[d][1]);
         } else {
