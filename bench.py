@@ -7,11 +7,15 @@ Workload (config.workload): BASELINE.json configs[1] "C2" — milk-jug-shaped sy
 2048 rays x 128 samples (64 occupied-voxel + 64 around-depth), hash grid L=16 T=2^19 finest 256, MLP = the reference
 NeRFSmall (SDF 2x64, colour 3x64), AMP on, pose refinement on. A step = one NerfRunner.train_loop (gather batch from the
 ray pool -> pose correction -> ray march -> fused forward/loss/backward -> pose backward -> Adam).
-  value : rays/s with the ray pool resident in HBM, CUDA-event timed over exactly K steps (max over ranks).
+  value : rays/s with the ray pool resident in HBM: blocks of K steps (NerfRunner.train_steps: one CUDA graph per 10 steps, batch
+          cursor on the device) x R repetitions, each block CUDA-event timed between barrier + synchronize; median of the max over ranks.
   e2e   : same metric through the public API from HOST buffers: every step copies its batch from pinned host memory
           (what the reference does after add_new_frames, nerf_runner.py:431: rays live on the CPU) and reads the loss back.
-  roofline : the fused step kernel alone, algorithmic bytes P*64*L*C + N*60 / its mean launch time.
-  cpu_baseline : the oracle port (oracle/nof_oracle.py, torch fp32 on all host cores) on a bounded sample.
+  roofline : the fused step kernel alone, algorithmic bytes P*64*L*C + N*60 (SURVEY.md 8d) / its mean launch time (`achieved`, `frac`);
+          the whole step incl. the 34 B/param Adam stream (`achieved_step`, `frac_step`); `traffic` = ncu dram bytes of this config.
+  cpu_baseline : the oracle port (oracle/nof_oracle.py, torch fp32 on all host cores) at the workload's full batch (fewer steps).
+  reference_cuda : the reference's own train_loop + its own CUDA extensions (oracle/_ref) on the same GPU (rank 0, N=1 only).
+  config4 : under torchrun, additionally BASELINE.json configs[3] = C3 x N sequences.
 Multi-GPU (torchrun): one independent sequence per rank, NCCL only for barrier + gather of the timings ("weak" scaling).
 """
 import argparse
@@ -351,6 +355,7 @@ def measure_config(args, c, name, rank, world, local_rank, dev, with_kernel=True
     # does its own H2D (N*48 B) and D2H (32 B) inside the timed region, through NerfRunner.train_loop.
     pool_host = runner.rays.cpu().pin_memory()
     stages = [torch.empty(N, 12).pin_memory() for _ in range(2)]
+    pool_np, stages_np = pool_host.numpy(), [t.numpy() for t in stages]
     dev_bufs = [torch.empty(N, 12, device=dev) for _ in range(2)]
     loss_host = [torch.zeros(8).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
@@ -364,7 +369,7 @@ def measure_config(args, c, name, rank, world, local_rank, dev, with_kernel=True
     def prefetch(slot):
         runner.data_loader.next_ids()                   # advances the epoch permutation; batch_ray_ids is its CPU slice
         ev_copy[slot].synchronize()                     # the previous upload from this pinned stage has finished
-        torch.index_select(pool_host, 0, runner.data_loader.batch_ray_ids, out=stages[slot])
+        np.take(pool_np, runner.data_loader.batch_ray_ids.numpy(), axis=0, out=stages_np[slot])     # one host thread (an OpenMP fork per step costs more than the gather)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_used[slot])       # the step that read dev_bufs[slot] two steps ago is done with it
             dev_bufs[slot].copy_(stages[slot], non_blocking=True)
