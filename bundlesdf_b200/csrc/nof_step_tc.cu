@@ -58,7 +58,7 @@ __host__ __device__ inline Plan make_plan(int KE) {
   s.d_o = take(PT * 16 * 2);
   s.out = take(PT * 4 * 4);
   s.zs = take(5 * DES * 4);                  // z, valid flag and u[3] of every point, in the scatter's padded order
-  s.rays = take(MAX_R * (int)sizeof(RayT));
+  s.rays = take(2 * MAX_R * (int)sizeof(RayT));    // two tiles' rays: the next tile's are staged while this one computes
   s.bar = take(64);                          // [0] TMA staging barrier, [1] MMA completion barrier
   s.tmem = take(16);
 #ifdef NOF_EXP_STAGE_L0   // ablation: level 0 of the fp16 table (17^3 entries) staged in shared memory by TMA
@@ -194,13 +194,13 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   float* sB = reinterpret_cast<float*>(smem + sp.bias);
   float* sOut = reinterpret_cast<float*>(smem + sp.out);
   float* sZ = reinterpret_cast<float*>(smem + sp.zs);
-  RayT* sRay = reinterpret_cast<RayT*>(smem + sp.rays);
+  RayT* sRayBase = reinterpret_cast<RayT*>(smem + sp.rays);
   const LevelS& lv = *reinterpret_cast<const LevelS*>(smem + sp.lv);
   const __half* sW3v = reinterpret_cast<const __half*>(smem + sp.w3v);
   uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem + sp.bar);
   uint64_t* bar_mma = bar_tma + 1;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + sp.tmem);
-  int* s_next = reinterpret_cast<int*>(s_tmem + 1);
+  int* s_next = reinterpret_cast<int*>(s_tmem + 1);          // [2]: the tile after the current one, by buffer parity
   const uint32_t sbase = smem_u32(smem);
   const uint32_t aW1 = sbase + sp.w1, aW2 = sbase + sp.w2, aW3 = sbase + sp.w3, aW4 = sbase + sp.w4, aW5 = sbase + sp.w5;
   const uint32_t aX0 = sbase + sp.x0, aX1 = sbase + sp.x1, aXC = sbase + sp.xc, aX3 = sbase + sp.x3, aX4 = sbase + sp.x4, aDO = sbase + sp.d_o;
@@ -291,12 +291,16 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   // 2048 tiles over 296 CTAs of uneven cost (invalid samples skip gather and scatter): -8.5 % vs the static round-robin. Starting
   // the second CTA of each SM half a tile late was tried and does not help.
   int* tile_ticket = reinterpret_cast<int*>(static_cast<char*>(a.wpack) + kWPackBytes - 16);
-  for (int grp = blockIdx.x; grp < a.n_groups;) {
-    // ============ 1. ray setup
-    if (tid < R) setup_ray(sRay[tid], a, grp * R + tid);
-    if (tid == NT - 1) *s_next = (int)gridDim.x + atomicAdd(tile_ticket, 1);
-    __syncthreads();
-    grp = *s_next;                                          // the NEXT tile (this one's rays are already staged)
+  // Ray state is double-buffered: while tile t computes, the warps that idle through its compositing / loss phases stage the rays of
+  // tile t+1 (one thread per ray: dependent global loads, ~1.5 us that used to sit in front of every tile behind a block barrier).
+  int grp = blockIdx.x, cur = 0;
+  if (tid < R && grp < a.n_groups) setup_ray(sRayBase[tid], a, grp * R + tid);
+  __syncthreads();
+  while (grp < a.n_groups) {
+    RayT* sRay = sRayBase + cur * MAX_R;
+    RayT* sRayNext = sRayBase + (cur ^ 1) * MAX_R;
+    // ============ 1. the next tile's ticket; this tile's rays were staged during the previous tile (or above)
+    if (tid == NT - 1) s_next[cur] = (int)gridDim.x + atomicAdd(tile_ticket, 1);
     // the rays' share of the colour net's first layer (their view / frame-feature inputs are the same for every sample): W3[:, views] . views,
     // on the fp16-rounded inputs autocast would feed; read as a per-ray bias by the layer-3 epilogue, several barriers from here
     for (int i = tid; i < R * 64; i += NT) {
@@ -432,9 +436,8 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) sOut[pt * 4 + c] = __half2float(__float2half_rn(v[c] + sB[208 + c]));
     }
-    tc_fence_before();
-    __syncthreads();                                        // (B) sumw / anyvalid complete, sOut rows visible
-    // ============ 4. compositing — once per point (owner threads)
+    // ============ 4. compositing — once per point (owner threads: warps 0-3). sumw / anyvalid were completed many barriers ago and every
+    // owner reads back only the sOut row it wrote itself, so no block barrier here; the other four warps stage the NEXT tile's rays meanwhile.
     float out4[4] = {0.f, 0.f, 0.f, 0.f};
     float w = 0.f;
     if (owner) {
@@ -448,8 +451,11 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) atomicAdd(&sRay[rl].rgb[c], pr[c]);
       }
+      named_bar_sync(1, PT);                                // (C) rgb_map complete — the four owner warps only
+    } else {
+      const int ng = s_next[cur];                           // written at the top of this tile, several block barriers ago
+      if (pt < R && ng < a.n_groups) setup_ray(sRayNext[pt], a, ng * R + pt);
     }
-    __syncthreads();                                        // (C) rgb_map complete
     // ============ 5. loss seeds
     float dsdf_s = 0.f;
     if (owner) {
@@ -730,7 +736,10 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
         }
       }
     }
-    __syncthreads();
+    // no barrier here: the next tile works on the other ray buffer, and everything else it overwrites (sZ, X0, the Jacobian slot) was last
+    // read before the barrier above
+    grp = s_next[cur];
+    cur ^= 1;
   }
 
   // ============ flush

@@ -452,7 +452,7 @@ class NerfRunner:
         self._step_buf = b
         return b
 
-    def _forward_backward(self, batch, t_rand=None, taps=None, before_fused=None, gather=False):
+    def _forward_backward(self, batch, t_rand=None, taps=None, before_fused=None, gather=False, after_fused=None):
         """Launches the step prologue (pose correction of all frames; with `gather` also the batch gather from the ray pool at the
         data loader's device cursor, into `batch`), the ray march and the fused forward+loss+backward for `batch` [N,12].
         Gradients accumulate into the flat grad buffers (scaled by the loss scale); nothing synchronises."""
@@ -477,6 +477,8 @@ class NerfRunner:
         if before_fused is not None:
             before_fused()
         sb.launch()                                         # zeroes b['losses'] and b['grad_tf'] itself
+        if after_fused is not None:
+            after_fused()
         if pa is not None:
             # the pose gradient stays multiplied by the loss scale like every other segment: nof_adam_step unscales ONCE
             # (GradScaler.unscale_, nerf_runner.py:756-760)
@@ -510,21 +512,31 @@ class NerfRunner:
         self.lr_table_dev.copy_(self.lr_dev[:1])            # the update issued at the end of the CURRENT step uses the current rate
 
     def synchronize_parameters(self):
-        """Apply a pending (deferred) table update. Called by every method that exposes the table; call it yourself before reading
+        """Apply a pending table update. Called by every method that exposes the table; call it yourself before reading
         `models['embed_fn'].embeddings` or the optimizer state directly when cfg['defer_table_update'] is on."""
-        if self._table_pending:
+        if self._table_pending == 'deferred':
             self._table_update()
-            self._table_pending = False
+        elif self._table_pending == 'inflight':
+            torch.cuda.current_stream().wait_stream(self._table_stream)
+        self._table_pending = False
 
-    def _step(self, batch, t_rand=None, gather=False):
-        """Forward, backward and optimizer of one step on the current stream (also what the CUDA graphs capture)."""
+    def _step(self, batch, t_rand=None, gather=False, overlap=False):
+        """Forward, backward and optimizer of one step on the current stream (also what the CUDA graphs capture).
+
+        cfg['defer_table_update']: the table's Adam pass (310 MB of HBM traffic at C2, the only part of the step that is bandwidth-bound)
+        runs on a side stream next to the latency-bound kernels around it. Two placements:
+          overlap=True   issued right after THIS step's fused kernel ('inflight'): runs next to pose backward, the small segments' Adam
+                         and the next step's prologue / ray march / operand pack; the next fused kernel joins it. Needs the next step
+                         in the same stream order or the same CUDA graph, so the captured blocks use it for all but their last step.
+          overlap=False  left to the NEXT step ('deferred'), which issues it first thing next to its own prologue / ray march: the only
+                         placement that overlaps across a graph boundary (single-step graphs, last step of a block)."""
         if not self._defer:
             b = self._forward_backward(batch, t_rand=t_rand, gather=gather)
             self._optimizer_step()
             return b
         main = torch.cuda.current_stream()
         pending, side = self._table_pending, self._table_stream
-        if pending:                                         # fork: table update of the PREVIOUS step
+        if pending == 'deferred':                           # fork: table update of the PREVIOUS step
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 self._table_update()
@@ -532,15 +544,29 @@ class NerfRunner:
         def join():                                         # the fused kernel is the first reader of the table
             if pending:
                 main.wait_stream(side)
-            else:
+            if not overlap and pending != 'deferred':       # this step's update is issued by the next step: keep this step's rate for it
                 self.lr_table_dev.copy_(self.lr_dev[:1])
 
-        b = self._forward_backward(batch, t_rand=t_rand, before_fused=join, gather=gather)
+        step, scale, inf = self._adam_scalars()
+
+        def fork():                                         # the table's gradient is complete: start its Adam pass now
+            if overlap:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    seg = dict(self.adam_segs['table'], lr=self.optimizer.param_groups[0]['lr'], lr_ptr=self.lr_dev[:1].data_ptr())
+                    ops.adam_update([seg], 0.9, 0.999, 1e-15, step, scale, inf)
+
+        b = self._forward_backward(batch, t_rand=t_rand, before_fused=join, gather=gather, after_fused=fork)
         groups = self.optimizer.param_groups
         small = [dict(s, lr=groups[s['group']]['lr']) for k, s in self.adam_segs.items() if k != 'table']
-        step, scale, inf = self._adam_scalars()
         ops.adam_update(small, 0.9, 0.999, 1e-15, step, scale, inf)
-        self._table_pending = True
+        if overlap:
+            side.wait_stream(main)                          # the bookkeeping follows BOTH updates (they read step / scale / found_inf)
+            with torch.cuda.stream(side):
+                ops.adam_finish(0.9, 0.999, step, scale, inf, tick=self.tick)
+            self._table_pending = 'inflight'
+        else:
+            self._table_pending = 'deferred'
         return b
 
     def _graph_usable(self, t_rand):
@@ -562,8 +588,8 @@ class NerfRunner:
         side.wait_stream(torch.cuda.current_stream())
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side):
-            for _ in range(n_steps):
-                self._step(static, gather=gather)
+            for i in range(n_steps):
+                self._step(static, gather=gather, overlap=(i + 1 < n_steps))
         self._graph[key] = g = dict(graph=graph, batch=static, buf=self._step_buf)
         return g
 
@@ -583,7 +609,7 @@ class NerfRunner:
             g['batch'].copy_(batch)
         g['graph'].replay()
         if self._defer:
-            self._table_pending = True
+            self._table_pending = 'deferred'
         self._step_buf = g['buf']                           # the buffers the graph writes (a render() may have swapped them)
         return g['buf']
 
@@ -639,7 +665,7 @@ class NerfRunner:
                     g = self._capture(key, k, gather=True)  # capturing does not execute: replay below runs these k steps
                 g['graph'].replay()
                 if self._defer:
-                    self._table_pending = True
+                    self._table_pending = 'deferred'
                 self._step_buf = g['buf']
             dl.consumed(k)
             self.global_step += k - 1                       # the host acts once, after the block's last step
@@ -724,15 +750,29 @@ class NerfRunner:
     def _model_args(self):
         return self._ensure_step_buffers(self.cfg['N_rand'])['sb']
 
-    @torch.no_grad()
     def run_network_density(self, inputs, get_normals=False):
-        """nerf_runner.py:1307-1347 (SDF only): inputs [..,3] in normalised space -> sdf [..,1]."""
+        """nerf_runner.py:1307-1347: inputs [..,3] in normalised space (clipped to [-1,1]) -> (sdf [..,1], valid [P]); with get_normals the
+        output is [..,4] = sdf | d sdf / d x (:1342-1345). The plain query runs on the native query kernel; the normals take the reference's
+        own route — the op-level grid encoder with dy_dx (nof_grid_encode_forward / _backward) and torch autograd through forward_sdf."""
         self.synchronize_parameters()
-        if get_normals:
-            raise NotImplementedError('normals from run_network_density are not built')
-        flat = inputs.reshape(-1, 3).float().contiguous().to(self.device)
-        sdf = ops.query_sdf(self._model_args(), flat)
-        return sdf.reshape(list(inputs.shape[:-1]) + [1]), torch.ones(len(flat), dtype=torch.bool, device=self.device)
+        flat = inputs.reshape(-1, 3).float().to(self.device).clamp(-1, 1).contiguous()
+        ok = torch.ones(len(flat), dtype=torch.bool, device=self.device)
+        if not get_normals:
+            with torch.no_grad():
+                sdf = ops.query_sdf(self._model_args(), flat)
+            return sdf.reshape(list(inputs.shape[:-1]) + [1]), ok
+        amp = bool(self.cfg['amp'])
+        with torch.enable_grad():
+            x = flat.detach().requires_grad_(True)
+            with torch.autocast('cuda', enabled=amp):
+                emb = self.models['embed_fn'](x)
+            emb = emb.float()
+            with torch.autocast('cuda', enabled=amp):
+                sdf = self.models['model'].forward_sdf(emb)
+            sdf = sdf.reshape(-1, 1).float()
+            normal = torch.autograd.grad(sdf, x, torch.ones_like(sdf))[0]
+        out = torch.cat((sdf.detach(), normal), dim=-1)
+        return out.reshape(list(inputs.shape[:-1]) + [4]), ok
 
     @torch.no_grad()
     def extract_mesh(self, level=None, voxel_size=0.003, isolevel=0.0, return_sigma=False):

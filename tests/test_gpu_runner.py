@@ -272,3 +272,35 @@ def test_pose_regulariser_follows_the_loss_scale():
     got = (g1 - g0)[1:] / scale
     assert torch.allclose(got, want, rtol=2e-2, atol=2e-3 * float(want.abs().max())), (got, want)
     assert float((g1 - g0)[0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('amp', [True, False])
+def test_run_network_density_normals_match_oracle(amp):
+    """run_network_density(get_normals=True) (nerf_runner.py:1342-1345): sdf | d sdf / d x through the op-level grid encoder's dy_dx and
+    autograd, against oracle.sdf_normals on the same parameters. fp32: 1e-4 of max|n|; AMP (fp16 table / dy_dx / activations): 3e-2."""
+    r, seq = _runner(amp, n_frames=4, N=256)
+    with torch.no_grad():
+        r.models['embed_fn'].embeddings.uniform_(-0.5, 0.5)
+        if r.table_f16 is not None:
+            r.table_f16.copy_(r.table)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(3000, 3, generator=g) * 2 - 1) * 0.98
+    out, ok = r.run_network_density(x.cuda(), get_normals=True)
+    assert out.shape == (3000, 4) and bool(ok.all())
+    plain, _ = r.run_network_density(x.cuda())
+    P = {k: v.detach().cpu() for k, v in r.models['model'].state_dict().items()}
+    P['embeddings'] = r.models['embed_fn'].embeddings.detach().cpu()
+    P['offsets'] = r.models['embed_fn'].offsets.cpu().numpy()
+    P['S'] = float(np.log2(r.models['embed_fn'].per_level_scale)); P['H'] = 16
+    sdf, n = O.sdf_normals(P, x, torch.ones(3000, dtype=torch.bool), half=amp)
+    rel = lambda a, w: np.abs(a - w).max() / max(np.abs(w).max(), 1e-30)
+    e = (rel(out[:, 0].cpu().numpy(), sdf.detach().numpy()), rel(plain[:, 0].cpu().numpy(), sdf.detach().numpy()))
+    assert e[0] < (5e-3 if amp else 1e-4) and e[1] < (5e-3 if amp else 1e-4), e
+    # The SDF is continuous but its gradient jumps across cell faces: a probe within fp32 rounding of a face of one of the 16 levels
+    # (3000 x 16 x 3 chances, ~1.5e-5 each at the finest level) may sit in the neighbouring cell in the other implementation. So the
+    # normals are compared point-wise: at least 99.5 % of the probes within tol of max|n|, and the typical probe far inside it.
+    nw = n.detach().numpy()
+    err = np.abs(out[:, 1:].cpu().numpy() - nw).max(axis=1) / np.abs(nw).max()
+    tol = 3e-2 if amp else 1e-4
+    print('run_network_density vs oracle: sdf %.3g / %.3g, normals median %.3g, within tol %.4f, max %.3g' % (e + (np.median(err), (err < tol).mean(), err.max())))
+    assert (err < tol).mean() > 0.995 and np.median(err) < tol / 5, (np.median(err), (err < tol).mean())
