@@ -263,8 +263,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   const int half = tid / PT;                 // gather/scatter: which half of the levels; epilogues: which half of the columns
   const int pt = tid - half * PT;            // = 32*(warp%4) + lane: the TMEM lane this thread may read
   const int rl = pt / Sp, sidx = pt - rl * Sp;
-  const int LH = (L + 1) >> 1;
-  const int l_beg = half ? LH : 0, l_end = half ? L : LH;
+  const int l_beg = half ? (L + 1) >> 1 : 0, l_end = half ? L : (L + 1) >> 1;
   const bool owner = half == 0;
   __half2* Jslot = reinterpret_cast<__half2*>(a.jws) + (size_t)blockIdx.x * (MAX_L * 3) * PT;
   const int g8 = lane >> 2, t4 = lane & 3;
@@ -334,7 +333,11 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
       }
     }
     // ============ 2. this thread's half of the gather
+#ifdef NOF_EXP_NO_GATHER
+    if (false) {
+#else
     if (valid) {
+#endif
 #pragma unroll 2
       for (int l = l_beg; l < l_end; ++l) {
         float enc[2], J[3][2];
@@ -607,11 +610,16 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
     // as ONE set of reductions per run: ~3.5x fewer operations on the L2 atomic unit, which is what bounds the scatter
     // (profiles/red_bench.cu: ~180 G lane-ops/s whatever the operand width).
     {
-      const int sg = lane & 15, l = 2 * warp + (lane >> 4);
+      const int sg = lane & 15;                             // (pairing coarse with fine levels in a warp to even out the runs per warp: +2.5 us)
+      const int l = 2 * warp + (lane >> 4);
       const int p0 = 8 * sg;
       const RayS& r8 = sRay[p0 / Sp];
       float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#ifdef NOF_EXP_NO_SCATTER
+      if (false) {
+#else
       if (l < L) {
+#endif
         const float scale = lv.scale[l];
         const uint32_t off = lv.off[l];
         const float* dE0 = reinterpret_cast<const float*>(pX3) + (size_t)(2 * l) * DES;

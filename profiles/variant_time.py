@@ -1,7 +1,9 @@
-"""Ablation for the north-star clause 'TMA staging of the hash table': level 0 of the fp16 table (17^3 entries, 19.7 KB) staged into shared
-memory by a TMA bulk copy in tc::step_tc_kernel and gathered from there (build with -DNOF_EXP_STAGE_L0 into bundlesdf_b200/lib_stage0).
-Prints the fused-step launch time at C2 and a parity check of the two builds against each other.
-    NOF_LIB=bundlesdf_b200/lib_stage0/libnof_sm100.so python profiles/stage_l0_ablation.py   vs   python profiles/stage_l0_ablation.py"""
+"""Fused-step launch time at C2 of a library variant, plus a checksum of its results (variants of one kernel must agree).
+    python -m bundlesdf_b200.build                                                      # default build -> bundlesdf_b200/lib
+    NOF_BUILD_DIR=bundlesdf_b200/lib_x NOF_EXTRA_FLAGS=-DNOF_EXP_... python -m bundlesdf_b200.build
+    python profiles/variant_time.py ; NOF_LIB=bundlesdf_b200/lib_x/libnof_sm100.so python profiles/variant_time.py
+Used for: -DNOF_EXP_STAGE_L0 (level 0 of the table staged in shared memory by TMA) and the component ablations -DNOF_EXP_NO_GATHER /
+NO_SCATTER / NO_RED / NO_WGRAD / NO_TC (one part of tc::step_tc_kernel compiled out: what the rest costs). Results in profiles/README.md."""
 import os, sys
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
