@@ -9,12 +9,15 @@
 //   * completion is signalled by tcgen05.commit on an mbarrier; every thread then pulls ITS row (32 columns of it) out of
 //     TMEM with tcgen05.ld.32x32b, applies bias / ReLU / the ReLU mask, converts to fp16 and writes the next operand;
 //   * activations and weights are stored in the canonical no-swizzle "core matrix" layout (8 rows x 16 bytes contiguous),
-//     which serves as K-major A/B for the forward GEMMs AND as MN-major B for the dgrad GEMMs (W is never transposed), and
-//     which ldmatrix(.trans) can read for the wgrad GEMMs that stay on mma.sync with register accumulators;
-//   * each dgrad MMA is issued asynchronously BEFORE the warps start the wgrad of the same layer, so the tensor-core
-//     generations overlap.
-// Ablation on B200 (profiles/README.md): the mma.sync + ldmatrix MLP phases cost 174 of 286 us per C2 launch; this kernel
-// replaces 156 of the 264 mma.sync and 152 of the 240 ldmatrix per warp and tile by 26 tcgen05.mma per CTA and tile.
+//     which serves as K-major A/B for the forward GEMMs, as MN-major B for the dgrad GEMMs (W is never transposed) AND as MN-major A and B
+//     for the weight-gradient GEMMs (dY^T X: the point index is the K dimension of both operands);
+//   * the weight gradients are tensor-core GEMMs too (M = 64, K = 128 points = 8 instructions per layer) whose accumulators STAY IN TMEM
+//     for the whole kernel (232 of the CTA's 256 columns) and are flushed to global memory once, at the end. Each is issued right behind the
+//     dgrad MMA of its layer by the same thread; the layer's epilogue waits for it only before it overwrites an operand. Bias gradients and
+//     the per-ray column sums of dY3 come out of the same GEMMs: the three B operands carry 8 extra columns holding the ray indicator
+//     (column r = 1 for the points of ray r). profiles/tc_issue.cu: one tcgen05.mma costs the issuing thread 46-49 cycles, whatever its shape.
+// Ablation on B200 (profiles/README.md): with the weight gradients on mma.sync + ldmatrix (register accumulators, previous version) they
+// cost 40 of the kernel's 204 us at C2.
 #include "nof_mlp_image.cuh"
 
 namespace nof {
@@ -33,6 +36,13 @@ __device__ __forceinline__ bool mbar_wait_inl(uint64_t* bar, uint32_t parity) {
 }
 
 constexpr int PT = 128, NT = 256, NWARP = 8;
+#ifndef NOF_TC_GATHER_UNROLL
+#define NOF_TC_GATHER_UNROLL 2                   // levels in flight per thread in the gather
+#endif
+#define NOF_PRAGMA(x) _Pragma(#x)
+#define NOF_UNROLL(n) NOF_PRAGMA(unroll n)
+constexpr int HB = 64 + 8;                        // row length of a 64-wide activation buffer that carries the ray indicator
+constexpr int TM_COLS = 256;                     // TMEM columns per CTA: 64 activations + 232 weight-gradient accumulators, two CTAs per SM
 constexpr int DES = PT + PT / 8;                 // padded point stride of the transposed dEnc / z arrays: index pt + pt/8
 __device__ __forceinline__ int des_idx(int pt) { return pt + (pt >> 3); }
 
@@ -50,16 +60,16 @@ __host__ __device__ inline Plan make_plan(int KE) {
   s.w1 = ip.w1; s.w2 = ip.w2; s.w3 = ip.w3g; s.w4 = ip.w4; s.w5 = ip.w5; s.bias = ip.bias; s.w3v = ip.w3v; s.lv = ip.lv; s.img_bytes = ip.bytes;
   int o = ip.bytes;
   auto take = [&](int bytes) { int r = o; o += (bytes + 127) / 128 * 128; return r; };
-  s.x0 = take(PT * KE * 2);
+  s.x0 = take(PT * (KE + 8) * 2);            // + 8 columns: ray indicator (the B operand of wgrad 1 ends with it)
   s.x1 = take(PT * 64 * 2);
-  s.xc = take(PT * KG * 2);                  // geo features (15 + pad): the only per-sample input of the colour net
-  s.x3 = take(PT * 64 * 2);                 // x3|x4 also hold dEnc fp32 [KE][DES] (transposed) at the end of the backward
+  s.xc = take(PT * (KG + 8) * 2);            // geo features (15 + pad): the only per-sample input of the colour net; + indicator
+  s.x3 = take(PT * HB * 2);                  // + indicator; also holds dEnc fp32 [KE][DES] (transposed) at the end of the backward
   s.x4 = take(PT * 64 * 2);
   s.d_o = take(PT * 16 * 2);
   s.out = take(PT * 4 * 4);
   s.zs = take(5 * DES * 4);                  // z, valid flag and u[3] of every point, in the scatter's padded order
   s.rays = take(2 * MAX_R * (int)sizeof(RayT));    // two tiles' rays: the next tile's are staged while this one computes
-  s.bar = take(64);                          // [0] TMA staging barrier, [1] MMA completion barrier
+  s.bar = take(64);                          // [0] TMA staging barrier, [1] forward/dgrad MMA completion, [2] wgrad MMA completion
   s.tmem = take(16);
 #ifdef NOF_EXP_STAGE_L0   // ablation: level 0 of the fp16 table (17^3 entries) staged in shared memory by TMA
   s.l0 = take(4920 * 4);
@@ -70,99 +80,42 @@ __host__ __device__ inline Plan make_plan(int KE) {
   return s;
 }
 
-// wgrad on mma.sync reading core-matrix buffers (same balanced split as nof_step_amp.cu): dW[strip*16..+16][nt0*8..] += dY^T X
-// RSUM: the column sums of dY (which the bias gradient needs anyway) are also added, ray by ray (ks_per_ray k-steps each), to cr of
-// the tile's rays: lanes with t4 == 0 hold rows g8 and g8 + 8 of the strip.
-// and dW3[:, views] += c_r (x) views goes into w3v (rows g8 / g8 + 8 of the strip, view columns t4, t4 + 4, ...: every lane of a quad holds the
-// same row sums, so the four lanes split the columns).
-template <int NTU, bool RSUM = false>
-__device__ __forceinline__ void wgrad_item(uint32_t dY, int Ky, uint32_t X, int Kx, int strip, int nt0, float (*acc)[4], float* bias2,
-                                           bool do_bias, int lane, RayT* rays = nullptr, int ks_per_ray = 8, float (*w3v)[2] = nullptr, int V = 0) {
+// One weight-gradient GEMM on the tensor core: D[64 x N] (+)= A^T B over the tile's 128 points. Both operands are [128 points x cols]
+// core-matrix buffers read MN-major (M / N run along the columns, K = the point index along the rows): A's first 64 columns, B's first N.
+// RA / RB: row lengths of the two buffers. The accumulator (M = 64: rows 16q .. 16q+15 live in lanes 0..15 of TMEM lane quadrant q) is
+// never cleared between tiles: `fresh` only on the CTA's first tile.
+template <int N>
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t a_addr, int RA, uint32_t b_addr, int RB, bool fresh) {
+  constexpr uint32_t idesc = umma_idesc(64, N, 1, 1);
 #ifdef NOF_EXP_NO_WGRAD
   return;
 #endif
-  const uint32_t ones = 0x3C003C00u;
-  const int pa = (lane & 7) + (lane >> 4) * 8, oa = strip * 16 + ((lane >> 3) & 1) * 8;       // A: rows p, cols o (dY^T)
-  const int pb = (lane & 7) + ((lane >> 3) & 1) * 8, ib = (lane >> 4) * 8;                      // B: rows p, cols i
-  float r0 = 0.f, r1 = 0.f;
+#pragma unroll
   for (int ks = 0; ks < PT / 16; ++ks) {
-    uint32_t a[4];
-    ldsm_x4_t(a, dY + cm_off(ks * 16 + pa, oa, Ky));
+    const uint64_t ad = umma_desc(a_addr + ks * 2 * (RA * 16), RA * 16, 128);              // MN-major: LBO = 8-row group stride, SBO = 8-column group stride
+    const uint64_t bd = umma_desc(b_addr + ks * 2 * (RB * 16), RB * 16, 128);
+    umma_f16(tmem_d, ad, bd, idesc, (ks > 0 || !fresh) ? 1u : 0u);
+  }
+}
+
+// End of the kernel: one [64 x NC] accumulator block out of TMEM into the global gradient. Thread (quadrant q, lane < 16) owns row
+// 16q + lane; warps q and q + 4 split the columns. addr(row, col) returns the destination (nullptr: padding, skip).
+template <int NC, class F>
+__device__ __forceinline__ void flush_tmem(uint32_t tq, int col0, int warp, int lane, F addr) {
+  static_assert(NC % 8 == 0, "flush_tmem");
+  const int row = (warp & 3) * 16 + lane;
+#pragma unroll 1
+  for (int c = (warp >> 2) * 8; c < NC; c += 16) {
+    float v[8];
+    TmemLd<8>::ld(tq + col0 + c, v);                       // warp-collective: lanes >= 16 read unused TMEM lanes
+    if (lane < 16) {
 #pragma unroll
-    for (int np = 0; np < (NTU + 1) / 2; ++np) {
-      uint32_t b[4];
-      ldsm_x4_t(b, X + cm_off(ks * 16 + pb, (nt0 + np * 2) * 8 + ib, Kx));
-      mma16816(acc[np * 2], a, b[0], b[1]);
-      if (np * 2 + 1 < NTU) mma16816(acc[np * 2 + 1], a, b[2], b[3]);
-    }
-    if (do_bias) {
-      float t[4] = {0.f, 0.f, 0.f, 0.f};
-      mma16816(t, a, ones, ones);
-      bias2[0] += t[0];
-      bias2[1] += t[2];
-      if (RSUM) {
-        r0 += t[0];
-        r1 += t[2];
-        if ((ks + 1) % ks_per_ray == 0) {
-          RayT& rq = rays[ks / ks_per_ray];
-          if ((lane & 3) == 0) {                                // one strip <-> one warp: plain stores, no atomics
-            rq.cr[strip * 16 + (lane >> 2)] = r0;
-            rq.cr[strip * 16 + (lane >> 2) + 8] = r1;
-          }
-#pragma unroll
-          for (int k = 0; k < 5; ++k) {
-            const int v = (lane & 3) + 4 * k;
-            if (v < V) {
-              const float hv = __half2float(__float2half_rn(rq.views[v]));
-              w3v[k][0] = fmaf(r0, hv, w3v[k][0]);
-              w3v[k][1] = fmaf(r1, hv, w3v[k][1]);
-            }
-          }
-          r0 = r1 = 0.f;
-        }
+      for (int j = 0; j < 8; ++j) {
+        float* dst = addr(row, c + j);
+        if (dst && v[j] != 0.f) red_add(dst, v[j]);
       }
     }
   }
-}
-template <int NS, int NTL>
-struct WSplit {
-  static constexpr int ideal = (NS * NTL + NWARP - 1) / NWARP;
-  static constexpr int CNT = ideal <= 1 ? 1 : (ideal <= 2 ? (NTL % 2 == 0 ? 2 : NTL) : (NTL % 4 == 0 ? 4 : NTL));
-  static constexpr int GROUPS = NTL / CNT;
-  static constexpr int ITEMS = NS * GROUPS;
-  static_assert(CNT <= 4 && NTL % CNT == 0, "wgrad split");
-};
-template <int CNT>
-__device__ __forceinline__ void flush_item(float* G, int wofs, int bofs, int ncols, int nrows, int strip, int nt0, const float (*acc)[4],
-                                           const float* bias2, bool has_bias, int g8, int t4, int ld = -1, int kofs = 0) {
-  if (ld < 0) ld = ncols;
-#pragma unroll
-  for (int nt = 0; nt < CNT; ++nt)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int o = strip * 16 + g8 + h * 8, i = (nt0 + nt) * 8 + 2 * t4;
-      const float v0 = acc[nt][h * 2], v1 = acc[nt][h * 2 + 1];
-      if (o >= nrows || i >= ncols) continue;
-      const size_t e = (size_t)wofs + (size_t)o * ld + kofs + i;
-      if (i + 1 < ncols && (reinterpret_cast<uintptr_t>(G + e) & 7u) == 0u) {                       // the fragment's two columns in one 8-byte reduction
-        if (v0 != 0.f || v1 != 0.f) red_add_v2(G + e, v0, v1);
-      } else {
-        if (v0 != 0.f) red_add(G + e, v0);
-        if (i + 1 < ncols && v1 != 0.f) red_add(G + e + 1, v1);
-      }
-    }
-  if (has_bias && t4 == 0) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int o = strip * 16 + g8 + h * 8;
-      if (o < nrows && bias2[h] != 0.f) red_add(G + bofs + o, bias2[h]);
-    }
-  }
-}
-template <int N>
-__device__ __forceinline__ void zero_acc(float (*acc)[4]) {
-#pragma unroll
-  for (int nt = 0; nt < N; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 }
 
 // One GEMM D[128 x N] (+)= A[128 x K] * B on the tensor core. A: core-matrix K-major buffer with row length KA.
@@ -199,6 +152,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   const __half* sW3v = reinterpret_cast<const __half*>(smem + sp.w3v);
   uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem + sp.bar);
   uint64_t* bar_mma = bar_tma + 1;
+  uint64_t* bar_wg = bar_tma + 2;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + sp.tmem);
   int* s_next = reinterpret_cast<int*>(s_tmem + 1);          // [2]: the tile after the current one, by buffer parity
   const uint32_t sbase = smem_u32(smem);
@@ -215,10 +169,11 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   if (tid == 0) {
     mbar_init(bar_tma, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_wg, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(64u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -245,19 +200,25 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   fence_async_smem();
   __syncthreads();
 
-  using S1 = WSplit<4, KE / 8>;
-  using S2 = WSplit<1, 8>;
-  using S3 = WSplit<4, KG / 8>;
-  using S4 = WSplit<4, 8>;
-  using S5 = WSplit<1, 8>;
-  float wg1[S1::CNT][4], wg2[S2::CNT][4], wg3[S3::CNT][4], wg4[S4::CNT][4], wg5[S5::CNT][4];
-  float wb1[2] = {0.f, 0.f}, wb2[2] = {0.f, 0.f}, wb3[2] = {0.f, 0.f}, wb4[2] = {0.f, 0.f}, wb5[2] = {0.f, 0.f};
-  zero_acc<S1::CNT>(wg1); zero_acc<S2::CNT>(wg2); zero_acc<S3::CNT>(wg3); zero_acc<S4::CNT>(wg4); zero_acc<S5::CNT>(wg5);
-  float w3v[5][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};       // dW3[:, views] rows g8 / g8+8 of this warp's strip, columns t4 + 4k
+  // TMEM columns: [0,64) activations / dgrad results; then the weight-gradient accumulators, kept for the whole kernel
+  //   D4 [64 out x (64 in | 8 ind)]   D1 [64 out x (KE in | 8 ind)]   D3 [64 out x (16 geo | 8 ind)]   D2^T [64 in x 16 out]   D5^T [64 in x 16 out]
+  constexpr int KEB = KE + 8, KGB = KG + 8;
+  constexpr int C4 = 64, C1 = C4 + HB, C3 = C1 + KEB, C2 = C3 + KGB, C5 = C2 + 16;
+  static_assert(C5 + 16 <= TM_COLS, "TMEM columns");
+  float wb2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // this thread's share of d b2 (its 8 columns of dH2, its point of every tile)
+  float wb2s = 0.f;                                              // owner threads: d b2[0] (the sdf column)
+  float wb5[3] = {0.f, 0.f, 0.f};                                // owner threads: d b5
+  float w3v[MAX_V];                                              // lanes < 16 of warps 0-3: row 16 q + lane of dW3[:, views]
+  float cr_prev[MAX_R];                                          // the same threads: cumulative per-ray column sums of dY3 up to the previous tile
+#pragma unroll
+  for (int v = 0; v < MAX_V; ++v) w3v[v] = 0.f;
+#pragma unroll
+  for (int r = 0; r < MAX_R; ++r) cr_prev[r] = 0.f;
   float loss_acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   float n_valid_s = 0.f, n_valid_r = 0.f;
   bool overflow = false;
-  uint32_t phase = 0;                        // parity of bar_mma
+  uint32_t phase = 0, phase_wg = 0;          // parities of bar_mma / bar_wg
+  bool fresh = true;                         // this CTA's first tile: the weight-gradient accumulators in TMEM start from zero
 
   const int Sp = a.Sp, R = a.R, S = a.p.S;
   const int half = tid / PT;                 // gather/scatter: which half of the levels; epilogues: which half of the columns
@@ -278,6 +239,20 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
     phase ^= 1u;
     tc_fence_after();
   };
+  auto wg_commit = [&]() {
+#ifndef NOF_EXP_NO_TC
+    umma_commit(bar_wg);
+#endif
+  };
+  // wait for the layer's weight-gradient MMAs: their operands may be overwritten, their accumulators read
+  auto wg_wait = [&]() {
+#ifdef NOF_EXP_NO_TC
+    return;
+#endif
+    tc_ok &= mbar_wait_inl(bar_wg, phase_wg);
+    phase_wg ^= 1u;
+    tc_fence_after();
+  };
   // publish this thread's shared-memory writes to the tensor core, retire its TMEM reads, block barrier
   auto sync_for_mma = [&]() {
     tc_fence_before();
@@ -292,6 +267,13 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   int* tile_ticket = reinterpret_cast<int*>(static_cast<char*>(a.wpack) + kWPackBytes - 16);
   // Ray state is double-buffered: while tile t computes, the warps that idle through its compositing / loss phases stage the rays of
   // tile t+1 (one thread per ray: dependent global loads, ~1.5 us that used to sit in front of every tile behind a block barrier).
+  // ray indicator (column r of the 8 extra B columns = 1 for the points of the tile's ray r): constant for the launch. X0's and XC's copies
+  // are written once; X3's is rewritten every tile (the region doubles as the dEnc buffer).
+  const uint4 ind_row = make_uint4((pt / Sp) == 0 ? 0x3C00u : ((pt / Sp) == 1 ? 0x3C000000u : 0u), (pt / Sp) == 2 ? 0x3C00u : ((pt / Sp) == 3 ? 0x3C000000u : 0u), 0u, 0u);
+  if (owner) {
+    *reinterpret_cast<uint4*>(pX0 + cm_off(pt, KE, KEB)) = ind_row;
+    *reinterpret_cast<uint4*>(pXC + cm_off(pt, KG, KGB)) = ind_row;
+  }
   int grp = blockIdx.x, cur = 0;
   if (tid < R && grp < a.n_groups) setup_ray(sRayBase[tid], a, grp * R + tid);
   __syncthreads();
@@ -338,7 +320,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
 #else
     if (valid) {
 #endif
-#pragma unroll 2
+      NOF_UNROLL(NOF_TC_GATHER_UNROLL)
       for (int l = l_beg; l < l_end; ++l) {
         float enc[2], J[3][2];
         if (a.p.need_pose_grad) {
@@ -352,16 +334,16 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
         } else {
           gather_level<true, false>(a.p.table_f16, lv, l, u, enc, J);
         }
-        *reinterpret_cast<uint32_t*>(pX0 + cm_off(pt, 2 * l, KE)) = pack_h2(enc[0], enc[1]);
+        *reinterpret_cast<uint32_t*>(pX0 + cm_off(pt, 2 * l, KEB)) = pack_h2(enc[0], enc[1]);
       }
     } else {
-      for (int l = l_beg; l < l_end; ++l) *reinterpret_cast<uint32_t*>(pX0 + cm_off(pt, 2 * l, KE)) = 0u;
+      for (int l = l_beg; l < l_end; ++l) *reinterpret_cast<uint32_t*>(pX0 + cm_off(pt, 2 * l, KEB)) = 0u;
     }
-    if (owner) for (int j = E; j < KE; j += 2) *reinterpret_cast<uint32_t*>(pX0 + cm_off(pt, j, KE)) = 0u;
+    if (owner) for (int j = E; j < KE; j += 2) *reinterpret_cast<uint32_t*>(pX0 + cm_off(pt, j, KEB)) = 0u;
     sync_for_mma();
     // ============ 3. MLP forward: five tcgen05 GEMMs, epilogue = this thread's row, its half of the columns
     // ---- L1: E -> 64, ReLU
-    if (tid == 0) issue_gemm<64, KE, 0>(tmem, aX0, KE, aW1, KE, bar_mma);
+    if (tid == 0) issue_gemm<64, KE, 0>(tmem, aX0, KEB, aW1, KE, bar_mma);
     mma_wait();
     {
       float v[32];
@@ -389,13 +371,13 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
         const int col = half * 8 + j;
         const __half hv = __float2half_rn(v[j] + sB[64 + col]);
         if (col == 0) sOut[pt * 4 + 3] = __half2float(hv);
-        else *reinterpret_cast<__half*>(pXC + cm_off(pt, col - 1, KG)) = hv;
+        else *reinterpret_cast<__half*>(pXC + cm_off(pt, col - 1, KGB)) = hv;
       }
-      if (!owner) *reinterpret_cast<__half*>(pXC + cm_off(pt, 15, KG)) = __float2half_rn(0.f);
+      if (!owner) *reinterpret_cast<__half*>(pXC + cm_off(pt, 15, KGB)) = __float2half_rn(0.f);
     }
     sync_for_mma();
     // ---- L3: geo 15 (+ the ray's view / feature share as a bias) -> 64, ReLU
-    if (tid == 0) issue_gemm<64, KG, 0>(tmem, aXC, KG, aW3, KG, bar_mma);
+    if (tid == 0) issue_gemm<64, KG, 0>(tmem, aXC, KGB, aW3, KG, bar_mma);
     mma_wait();
     {
       float v[32];
@@ -408,12 +390,13 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
           const int c = half * 32 + ch * 8 + 2 * j;
           w[j] = pack_h2(fmaxf(v[ch * 8 + 2 * j] + sB[80 + c] + rs.vb[c], 0.f), fmaxf(v[ch * 8 + 2 * j + 1] + sB[80 + c + 1] + rs.vb[c + 1], 0.f));
         }
-        *reinterpret_cast<uint4*>(pX3 + cm_off(pt, half * 32 + ch * 8, 64)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(pX3 + cm_off(pt, half * 32 + ch * 8, HB)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
+      if (owner) *reinterpret_cast<uint4*>(pX3 + cm_off(pt, 64, HB)) = ind_row;
     }
     sync_for_mma();
     // ---- L4: 64 -> 64, ReLU
-    if (tid == 0) issue_gemm<64, 64, 0>(tmem, aX3, 64, aW4, 64, bar_mma);
+    if (tid == 0) issue_gemm<64, 64, 0>(tmem, aX3, HB, aW4, 64, bar_mma);
     mma_wait();
     {
       float v[32];
@@ -488,67 +471,75 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
       const float s0 = d_out[0] * scale_ls, s1 = d_out[1] * scale_ls, s2 = d_out[2] * scale_ls;
       overflow |= !(fabsf(s0) <= 65504.f) || !(fabsf(s1) <= 65504.f) || !(fabsf(s2) <= 65504.f) || !(fabsf(dsdf_s) <= 65504.f);
       *reinterpret_cast<uint4*>(pDO + cm_off(pt, 0, 16)) = make_uint4(pack_h2(s0, s1), pack_h2(s2, 0.f), 0u, 0u);
+      wb5[0] += __half2float(__float2half_rn(s0)); wb5[1] += __half2float(__float2half_rn(s1)); wb5[2] += __half2float(__float2half_rn(s2));
       *reinterpret_cast<uint4*>(pDO + cm_off(pt, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
     }
     sync_for_mma();                                         // (S0) dOut visible to the warps and to the tensor core
 
-    // ============ 6. backward: per layer the dgrad MMA is issued first (async), the warps do the wgrad meanwhile
+    // ============ 6. backward: per layer the dgrad MMA, then the weight-gradient MMAs (8 k-steps over the tile's points) behind it in the same
+    // in-order pipe; the epilogue needs the first for its values and the second only before it overwrites an operand
     // ---- layer 5
-    if (tid == 0) issue_gemm<64, 16, 1>(tmem, aDO, 16, aW5, 64, bar_mma);
-    if (warp < S5::ITEMS) wgrad_item<S5::CNT>(aDO, 16, aX4, 64, 0, (warp % S5::GROUPS) * S5::CNT, wg5, wb5, (warp % S5::GROUPS) == 0, lane);
+    if (tid == 0) {
+      issue_gemm<64, 16, 1>(tmem, aDO, 16, aW5, 64, bar_mma);
+      issue_wgrad<16>(tmem + C5, aX4, 64, aDO, 16, fresh);  // D5^T [64 in x 16 out] += X4^T dOut
+      wg_commit();
+    }
     mma_wait();
     {
       float v[32];
       TmemLd<32>::ld(trow + half * 32, v);
-      tc_fence_before();
-      __syncthreads();                                      // every warp finished reading X4 (wgrad5) and its TMEM rows
+      uint32_t o[16];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        unsigned char* p = pX4 + cm_off(pt, half * 32 + ch * 8, 64);
-        const uint4 m = *reinterpret_cast<const uint4*>(p);
+        const uint4 m = *reinterpret_cast<const uint4*>(pX4 + cm_off(pt, half * 32 + ch * 8, 64));
         const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-        uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                         // packed: round the pair, mask it with (activation > 0), test the exponents
           const uint32_t keep = __hgt2_mask(*reinterpret_cast<const __half2*>(&mw[j]), __float2half2_rn(0.f));
-          o[j] = pack_h2(v[ch * 8 + 2 * j], v[ch * 8 + 2 * j + 1]) & keep;
-          overflow |= ((o[j] & 0x7C00u) == 0x7C00u) || ((o[j] & 0x7C000000u) == 0x7C000000u);
+          o[ch * 4 + j] = pack_h2(v[ch * 8 + 2 * j], v[ch * 8 + 2 * j + 1]) & keep;
+          overflow |= ((o[ch * 4 + j] & 0x7C00u) == 0x7C00u) || ((o[ch * 4 + j] & 0x7C000000u) == 0x7C000000u);
         }
-        *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
       }
+      wg_wait();                                            // wgrad 5 has read X4: only now may the operand be overwritten
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(pX4 + cm_off(pt, half * 32 + ch * 8, 64)) = make_uint4(o[ch * 4], o[ch * 4 + 1], o[ch * 4 + 2], o[ch * 4 + 3]);
     }
     sync_for_mma();                                         // dY4 visible
     // ---- layer 4
-    if (tid == 0) issue_gemm<64, 64, 1>(tmem, aX4, 64, aW4, 64, bar_mma);
-    if (warp < S4::ITEMS)
-      wgrad_item<S4::CNT>(aX4, 64, aX3, 64, warp / S4::GROUPS, (warp % S4::GROUPS) * S4::CNT, wg4, wb4, (warp % S4::GROUPS) == 0, lane);
+    if (tid == 0) {
+      issue_gemm<64, 64, 1>(tmem, aX4, 64, aW4, 64, bar_mma);
+      issue_wgrad<HB>(tmem + C4, aX4, 64, aX3, HB, fresh);   // D4 [64 out x (64 in | ind)] += dY4^T [X3 | ind]
+      wg_commit();
+    }
     mma_wait();
     {
       float v[32];
       TmemLd<32>::ld(trow + half * 32, v);
-      tc_fence_before();
-      __syncthreads();                                      // wgrad4 finished reading X3
+      uint32_t o[16];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        unsigned char* p = pX3 + cm_off(pt, half * 32 + ch * 8, 64);
-        const uint4 m = *reinterpret_cast<const uint4*>(p);
+        const uint4 m = *reinterpret_cast<const uint4*>(pX3 + cm_off(pt, half * 32 + ch * 8, HB));
         const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-        uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                         // packed: round the pair, mask it with (activation > 0), test the exponents
           const uint32_t keep = __hgt2_mask(*reinterpret_cast<const __half2*>(&mw[j]), __float2half2_rn(0.f));
-          o[j] = pack_h2(v[ch * 8 + 2 * j], v[ch * 8 + 2 * j + 1]) & keep;
-          overflow |= ((o[j] & 0x7C00u) == 0x7C00u) || ((o[j] & 0x7C000000u) == 0x7C000000u);
+          o[ch * 4 + j] = pack_h2(v[ch * 8 + 2 * j], v[ch * 8 + 2 * j + 1]) & keep;
+          overflow |= ((o[ch * 4 + j] & 0x7C00u) == 0x7C00u) || ((o[ch * 4 + j] & 0x7C000000u) == 0x7C000000u);
         }
-        *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
       }
+      wg_wait();                                            // wgrad 4 has read X3: only now may the operand be overwritten
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(pX3 + cm_off(pt, half * 32 + ch * 8, HB)) = make_uint4(o[ch * 4], o[ch * 4 + 1], o[ch * 4 + 2], o[ch * 4 + 3]);
     }
     sync_for_mma();                                         // dY3 visible
     // ---- layer 3: dgrad -> dgeo (the view part needs no per-sample dgrad), wgrad dY3^T XG + the per-ray column sums of dY3
-    if (tid == 0) issue_gemm<KG, 64, 1>(tmem, aX3, 64, aW3, KG, bar_mma);
-    if (warp < S3::ITEMS)
-      wgrad_item<S3::CNT, true>(aX3, 64, aXC, KG, warp / S3::GROUPS, (warp % S3::GROUPS) * S3::CNT, wg3, wb3, (warp % S3::GROUPS) == 0, lane, sRay,
-                                Sp / 16, w3v, V);
+    if (tid == 0) {
+      issue_gemm<KG, 64, 1>(tmem, aX3, HB, aW3, KG, bar_mma);
+      issue_wgrad<KGB>(tmem + C3, aX3, HB, aXC, KGB, fresh);  // D3 [64 out x (16 geo | ind)] += dY3^T [XC | ind]
+      wg_commit();
+    }
     mma_wait();
     {
       float v[8];
@@ -558,47 +549,79 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
         const int col = half * 8 + j;
         if (col < 15) {
           overflow |= !(fabsf(v[j]) <= 65504.f);
-          *reinterpret_cast<__half*>(pDO + cm_off(pt, 1 + col, 16)) = __float2half_rn(v[j]);
+          const __half hv = __float2half_rn(v[j]);
+          *reinterpret_cast<__half*>(pDO + cm_off(pt, 1 + col, 16)) = hv;
+          wb2[j] += __half2float(hv);                       // d b2[1 + col]: what the tensor core would sum
         }
       }
-      if (owner) *reinterpret_cast<__half*>(pDO + cm_off(pt, 0, 16)) = __float2half_rn(dsdf_s);
+      if (owner) {
+        const __half hs = __float2half_rn(dsdf_s);
+        *reinterpret_cast<__half*>(pDO + cm_off(pt, 0, 16)) = hs;
+        wb2s += __half2float(hs);
+      }
+    }
+    wg_wait();                                              // wgrad 3: its indicator columns are the per-ray column sums of dY3
+    if (warp < 4) {
+      // c_r = sum over the ray's samples of dY3: the accumulator is cumulative over this CTA's tiles, so this tile's share is the difference
+      // to the previous read. Feeds d views (end of the tile) and dW3[:, views] += c_r (x) views.
+      float c8[8];
+      TmemLd<8>::ld(trow + C3 + KG, c8);
+      if (lane < 16) {
+        const int o = warp * 16 + lane;
+#pragma unroll
+        for (int r = 0; r < MAX_R; ++r) {
+          if (r < R) {
+            const float c = c8[r] - cr_prev[r];
+            cr_prev[r] = c8[r];
+            sRay[r].cr[o] = c;
+#pragma unroll
+            for (int vv = 0; vv < MAX_V; ++vv)
+              if (vv < V) w3v[vv] = fmaf(c, __half2float(__float2half_rn(sRay[r].views[vv])), w3v[vv]);
+          }
+        }
+      }
     }
     sync_for_mma();                                         // dH2 visible
     // ---- layer 2
-    if (tid == 0) issue_gemm<64, 16, 1>(tmem, aDO, 16, aW2, 64, bar_mma);
-    if (warp < S2::ITEMS) wgrad_item<S2::CNT>(aDO, 16, aX1, 64, 0, (warp % S2::GROUPS) * S2::CNT, wg2, wb2, (warp % S2::GROUPS) == 0, lane);
+    if (tid == 0) {
+      issue_gemm<64, 16, 1>(tmem, aDO, 16, aW2, 64, bar_mma);
+      issue_wgrad<16>(tmem + C2, aX1, 64, aDO, 16, fresh);  // D2^T [64 in x 16 out] += X1^T dH2
+      wg_commit();
+    }
     mma_wait();
     {
       float v[32];
       TmemLd<32>::ld(trow + half * 32, v);
-      tc_fence_before();
-      __syncthreads();                                      // wgrad2 finished reading X1
+      uint32_t o[16];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        unsigned char* p = pX1 + cm_off(pt, half * 32 + ch * 8, 64);
-        const uint4 m = *reinterpret_cast<const uint4*>(p);
+        const uint4 m = *reinterpret_cast<const uint4*>(pX1 + cm_off(pt, half * 32 + ch * 8, 64));
         const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-        uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                         // packed: round the pair, mask it with (activation > 0), test the exponents
           const uint32_t keep = __hgt2_mask(*reinterpret_cast<const __half2*>(&mw[j]), __float2half2_rn(0.f));
-          o[j] = pack_h2(v[ch * 8 + 2 * j], v[ch * 8 + 2 * j + 1]) & keep;
-          overflow |= ((o[j] & 0x7C00u) == 0x7C00u) || ((o[j] & 0x7C000000u) == 0x7C000000u);
+          o[ch * 4 + j] = pack_h2(v[ch * 8 + 2 * j], v[ch * 8 + 2 * j + 1]) & keep;
+          overflow |= ((o[ch * 4 + j] & 0x7C00u) == 0x7C00u) || ((o[ch * 4 + j] & 0x7C000000u) == 0x7C000000u);
         }
-        *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
       }
+      wg_wait();                                            // wgrad 2 has read X1: only now may the operand be overwritten
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(pX1 + cm_off(pt, half * 32 + ch * 8, 64)) = make_uint4(o[ch * 4], o[ch * 4 + 1], o[ch * 4 + 2], o[ch * 4 + 3]);
     }
     sync_for_mma();                                         // dY1 visible
     // ---- layer 1: dgrad -> dEnc fp32 (X3 region, dead), wgrad dY1^T X0
-    if (tid == 0) issue_gemm<KE, 64, 1>(tmem, aX1, 64, aW1, KE, bar_mma);
-    if (warp < S1::ITEMS)
-      wgrad_item<S1::CNT>(aX1, 64, aX0, KE, warp / S1::GROUPS, (warp % S1::GROUPS) * S1::CNT, wg1, wb1, (warp % S1::GROUPS) == 0, lane);
+    if (tid == 0) {
+      issue_gemm<KE, 64, 1>(tmem, aX1, 64, aW1, KE, bar_mma);
+      issue_wgrad<KEB>(tmem + C1, aX1, 64, aX0, KEB, fresh);  // D1 [64 out x (KE in | ind)] += dY1^T [X0 | ind]
+      wg_commit();
+    }
     mma_wait();
     {
       constexpr int NH = KE / 2;                            // columns per thread
       float v[NH];
       TmemLd<NH>::ld(trow + half * NH, v);
-      float* dE = reinterpret_cast<float*>(pX3) + des_idx(pt);                 // transposed: [column][DES], spills into X4 (dead)
+      float* dE = reinterpret_cast<float*>(pX3) + des_idx(pt);                 // transposed: [column][DES] — exactly the X3 region (dY3 is dead)
 #pragma unroll
       for (int j = 0; j < NH; ++j) dE[(half * NH + j) * DES] = v[j];
     }
@@ -714,6 +737,8 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
         }
       }
     }
+    wg_wait();                                              // wgrad 1 (long finished): X0 / X1 may be rewritten by the next tile
+    fresh = false;
     __syncthreads();
     // rays of this tile: d views = W3[:, views]^T c_r -> frame-feature gradient and (through the SH Jacobian) the pose. Warp w looks after
     // ray w: lane v computes column v (64 multiply-adds, no shuffles), lane 0 finishes.
@@ -750,31 +775,48 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
     cur ^= 1;
   }
 
-  // ============ flush
-  {
+  // ============ flush: the weight-gradient accumulators leave TMEM once per CTA (9.1 k reductions, as the register version did)
+  if (!fresh) {
     float* G = a.p.grad_mlp;
     const int K3 = V + 15;
-    if (warp < S1::ITEMS)
-      flush_item<S1::CNT>(G, a.po[0], a.po[1], E, 64, warp / S1::GROUPS, (warp % S1::GROUPS) * S1::CNT, wg1, wb1, (warp % S1::GROUPS) == 0, g8, t4);
-    if (warp < S2::ITEMS)
-      flush_item<S2::CNT>(G, a.po[2], a.po[3], 64, 16, 0, (warp % S2::GROUPS) * S2::CNT, wg2, wb2, (warp % S2::GROUPS) == 0, g8, t4);
-    if (warp < S3::ITEMS)
-      flush_item<S3::CNT>(G, a.po[4], a.po[5], 15, 64, warp / S3::GROUPS, (warp % S3::GROUPS) * S3::CNT, wg3, wb3, (warp % S3::GROUPS) == 0, g8, t4, K3, V);
-    if (warp < S3::ITEMS && (warp % S3::GROUPS) == 0) {        // the strip owners hold dW3[:, views]
-      const int strip = warp / S3::GROUPS;
+    const int o = (warp & 3) * 16 + lane;                   // lanes < 16: the accumulator row this thread reads
+    tc_fence_after();
+    flush_tmem<64>(trow, C4, warp, lane, [&](int r, int c) { return G + a.po[6] + r * 64 + c; });
+    flush_tmem<KE>(trow, C1, warp, lane, [&](int r, int c) { return c < E ? G + a.po[0] + r * E + c : (float*)nullptr; });
+    flush_tmem<16>(trow, C3, warp, lane, [&](int r, int c) { return c < 15 ? G + a.po[4] + r * K3 + V + c : (float*)nullptr; });
+    flush_tmem<16>(trow, C2, warp, lane, [&](int r, int c) { return G + a.po[2] + c * 64 + r; });                          // transposed: row = input
+    flush_tmem<16>(trow, C5, warp, lane, [&](int r, int c) { return c < 3 ? G + a.po[8] + c * 64 + r : (float*)nullptr; });
+    if (warp < 4) {                                         // bias gradients = the indicator columns summed over the rays
+      float c4[8], c1[8];
+      TmemLd<8>::ld(trow + C4 + 64, c4);
+      TmemLd<8>::ld(trow + C1 + KE, c1);
+      if (lane < 16) {
+        float b4 = 0.f, b1 = 0.f, b3 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int v = t4 + 4 * k;
-        if (v < V) {
-          if (w3v[k][0] != 0.f) red_add(G + a.po[4] + (strip * 16 + g8) * K3 + v, w3v[k][0]);
-          if (w3v[k][1] != 0.f) red_add(G + a.po[4] + (strip * 16 + g8 + 8) * K3 + v, w3v[k][1]);
-        }
+        for (int r = 0; r < MAX_R; ++r)
+          if (r < R) { b4 += c4[r]; b1 += c1[r]; b3 += cr_prev[r]; }
+        if (b4 != 0.f) red_add(G + a.po[7] + o, b4);
+        if (b1 != 0.f) red_add(G + a.po[1] + o, b1);
+        if (b3 != 0.f) red_add(G + a.po[5] + o, b3);
+#pragma unroll
+        for (int vv = 0; vv < MAX_V; ++vv)
+          if (vv < V && w3v[vv] != 0.f) red_add(G + a.po[4] + o * K3 + vv, w3v[vv]);
       }
     }
-    if (warp < S4::ITEMS)
-      flush_item<S4::CNT>(G, a.po[6], a.po[7], 64, 64, warp / S4::GROUPS, (warp % S4::GROUPS) * S4::CNT, wg4, wb4, (warp % S4::GROUPS) == 0, g8, t4);
-    if (warp < S5::ITEMS)
-      flush_item<S5::CNT>(G, a.po[8], a.po[9], 64, 3, 0, (warp % S5::GROUPS) * S5::CNT, wg5, wb5, (warp % S5::GROUPS) == 0, g8, t4);
+    {                                                       // d b2, d b5: per-thread sums over this CTA's tiles -> warp -> global
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = warp_sum(wb2[j]);
+        if (lane == 0 && half * 8 + j < 15 && t != 0.f) red_add(G + a.po[3] + 1 + half * 8 + j, t);
+      }
+      const float ts = warp_sum(wb2s);
+      if (lane == 0 && ts != 0.f) red_add(G + a.po[3], ts);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float t = warp_sum(wb5[c]);
+        if (lane == 0 && t != 0.f) red_add(G + a.po[9] + c, t);
+      }
+    }
   }
   {
     loss_acc[0] = loss_acc[1] + loss_acc[2] + loss_acc[3] + loss_acc[4];
@@ -792,7 +834,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   // ---- release TMEM
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TM_COLS) : "memory");
 }
 
 }  // namespace tc
