@@ -409,7 +409,7 @@ def measure_config(args, c, name, rank, world, local_rank, dev, with_kernel=True
            'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': N * 12 * 4, 'd2h_bytes_per_step': 32, 'steps': K, 'reps': e2e_reps,
                    'ms_per_step': 1e3 * t_e2e / K, 'block_ms_min': 1e3 * min(e2e_blocks), 'block_ms_max': 1e3 * max(e2e_blocks)},
            'ray_pool': int(runner.rays.shape[0]), 'setup_s': round(t_setup, 1), 'n_params': n_params}
-    launches_per_step = (8 if DEFER_TABLE else 6) + (1 if c.get('eik', 0) > 0 else 0)   # prologue, ray march, operand pack, fused step, pose backward, Adam (1 | 3) [+ eikonal count pass]
+    launches_per_step = (7 if DEFER_TABLE else 6) + (1 if c.get('eik', 0) > 0 else 0)   # prologue, ray march, operand pack, fused step, pose backward, Adam (1 | 2: small segments + table, bookkeeping on the last block of either) [+ eikonal count pass]
     res['gpu_launches'] = launches_per_step * K * reps
     if not with_kernel:
         return res

@@ -65,6 +65,8 @@ _SIGS = {
     'nof_adam_step': (C.c_int, [C.POINTER(NofAdamSeg), C.c_int, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     'nof_adam_update': (C.c_int, [C.POINTER(NofAdamSeg), C.c_int, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
     'nof_adam_finish': (C.c_int, [_vp, _vp, _vp, _vp, _f32, _f32, _vp]),
+    'nof_adam_tile_count': (C.c_int, [C.POINTER(NofAdamSeg), C.c_int]),
+    'nof_adam_update_shared': (C.c_int, [C.POINTER(NofAdamSeg), C.c_int, _f32, _f32, _f32, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     'nof_query_sdf': (C.c_int, [C.POINTER(NofStep), _vp, _vp, _i64, _vp]),
     'nof_cloud_within_radius': (C.c_int, [_vp, _i64, _vp, _vp, _f32, _f32, C.c_int, _f32, _vp, _vp]),
     'nof_marching_tets_count': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32, _vp, _vp]),

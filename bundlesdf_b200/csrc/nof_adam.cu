@@ -79,7 +79,7 @@ __global__ void adam_finish_kernel(int32_t* step_ptr, float* scale_state, int32_
 #define NOF_ADAM_MINB 4
 #endif
 __global__ void __launch_bounds__(ADAM_THREADS, NOF_ADAM_MINB) adam_kernel(const AdamArgs a, int32_t* step_ptr, float* scale_state, int32_t* found_inf,
-                                                            unsigned long long* tick, int do_finish) {
+                                                            unsigned long long* tick, int finish_at) {
   const uint32_t tile = blockIdx.x;
   int si = 0;
 #pragma unroll
@@ -163,11 +163,13 @@ __global__ void __launch_bounds__(ADAM_THREADS, NOF_ADAM_MINB) adam_kernel(const
       }
     }
   }
-  // ---- the last CTA to get here does the scalar bookkeeping (every CTA has read step/scale/found_inf by then): saves a launch
-  if (step_ptr && do_finish) {
+  // ---- the last CTA to get here does the scalar bookkeeping (every CTA has read step/scale/found_inf by then): saves a launch.
+  // finish_at = the number of CTAs that have to pass: this launch's grid (nof_adam_step) or the sum over the launches that share one step's
+  // update (nof_adam_update_shared: e.g. the table segment on one stream and the small segments on another, in either order).
+  if (step_ptr && finish_at) {
     __syncthreads();                                        // every thread of this CTA has consumed the scalars (its stores depend on them)
     if (threadIdx.x == 0) {                                 // no fence: the bookkeeping touches nothing the other CTAs write
-      if (atomicAdd(step_ptr + 4, 1) == (int)gridDim.x - 1) {
+      if (atomicAdd(step_ptr + 4, 1) == finish_at - 1) {
         step_ptr[4] = 0;
         adam_finish(step_ptr, scale_state, found_inf, tick, a.beta1, a.beta2);
       }
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(ADAM_THREADS, NOF_ADAM_MINB) adam_kernel(const
 using namespace nof;
 
 static int adam_launch(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, float eps, int32_t* step, float* scale_state,
-                       int32_t* found_inf, uint64_t* tick, bool finish, const char* fn, nof_stream_t stream) {
+                       int32_t* found_inf, uint64_t* tick, bool finish, const char* fn, nof_stream_t stream, int shared_tiles = 0) {
   NOF_REQUIRE(segs && n_segs >= 1 && n_segs <= ADAM_MAX_SEGS, "%s: n_segs=%d (1..%d)", fn, n_segs, ADAM_MAX_SEGS);
   AdamArgs a;
   a.n_segs = n_segs;
@@ -204,7 +206,7 @@ static int adam_launch(const NofAdamSeg* segs, int n_segs, float beta1, float be
   cudaStream_t st = as_stream(stream);
   unsigned long long* tk = reinterpret_cast<unsigned long long*>(tick);
   if (tiles > 0) {
-    adam_kernel<<<(uint32_t)tiles, ADAM_THREADS, 0, st>>>(a, step, scale_state, found_inf, tk, finish ? 1 : 0);
+    adam_kernel<<<(uint32_t)tiles, ADAM_THREADS, 0, st>>>(a, step, scale_state, found_inf, tk, shared_tiles > 0 ? shared_tiles : (finish ? (int)tiles : 0));
     int rc = check_launch("adam_kernel");
     if (rc) return rc;
     if (step || !finish) return NOF_OK;                      // bookkeeping done by the kernel's last CTA / not asked for
@@ -229,4 +231,19 @@ extern "C" int nof_adam_finish(int32_t* step, float* scale_state, int32_t* found
                                nof_stream_t stream) {
   adam_finish_kernel<<<1, 1, 0, as_stream(stream)>>>(step, scale_state, found_inf, reinterpret_cast<unsigned long long*>(tick), beta1, beta2);
   return check_launch("adam_finish_kernel");
+}
+
+extern "C" int nof_adam_tile_count(const NofAdamSeg* segs, int n_segs) {
+  NOF_REQUIRE(segs && n_segs >= 1 && n_segs <= ADAM_MAX_SEGS, "nof_adam_tile_count: n_segs=%d (1..%d)", n_segs, ADAM_MAX_SEGS);
+  uint64_t tiles = 0;
+  for (int i = 0; i < n_segs; ++i) tiles += div_up<uint64_t>(segs[i].n, ADAM_TILE);
+  NOF_REQUIRE(tiles < 0x7fffffffull, "nof_adam_tile_count: too many elements");
+  return (int)tiles;
+}
+
+extern "C" int nof_adam_update_shared(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, float eps, int32_t* step, float* scale_state,
+                                      int32_t* found_inf, uint64_t* tick, int total_tiles, nof_stream_t stream) {
+  NOF_REQUIRE(step != nullptr, "nof_adam_update_shared: needs the step buffer (its completion counter)");
+  NOF_REQUIRE(total_tiles > 0, "nof_adam_update_shared: total_tiles=%d", total_tiles);
+  return adam_launch(segs, n_segs, beta1, beta2, eps, step, scale_state, found_inf, tick, false, "nof_adam_update_shared", stream, total_tiles);
 }

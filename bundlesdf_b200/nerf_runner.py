@@ -241,6 +241,7 @@ class NerfRunner:
         # update); everything that reads the table from outside goes through synchronize_parameters() first.
         self._defer = bool(self.cfg.get('defer_table_update', False))
         self._table_pending = False
+        self._adam_total_tiles = None
         self._table_stream = torch.cuda.Stream(priority=0) if self._defer else None
         self.march_tick = torch.zeros(1, dtype=torch.int64, device=dev)     # sampler RNG tick, bumped by every step prologue
         self._done_ticket = torch.zeros(1, dtype=torch.int32, device=dev)   # CTA completion ticket of nof_step_prologue
@@ -503,12 +504,23 @@ class NerfRunner:
         step, scale, inf = self._adam_scalars()
         ops.adam_step(segs, 0.9, 0.999, 1e-15, step, scale, inf, tick=self.tick)
 
-    def _table_update(self):
-        """The deferred half of an optimizer step: Adam on the table segment, then the step's bookkeeping."""
+    def _adam_shared(self, which, lr_ptr=None):
+        """One of the two launches of a step's optimizer update in the deferred mode ('table' | 'small'). They may run on different streams
+        in either order; whichever retires last does the step's bookkeeping (nof_adam_update_shared), so no launch sits behind them."""
         step, scale, inf = self._adam_scalars()
-        seg = dict(self.adam_segs['table'], lr=self.optimizer.param_groups[0]['lr'], lr_ptr=self.lr_table_dev.data_ptr())
-        ops.adam_update([seg], 0.9, 0.999, 1e-15, step, scale, inf)
-        ops.adam_finish(0.9, 0.999, step, scale, inf, tick=self.tick)
+        groups = self.optimizer.param_groups
+        if which == 'table':
+            segs = [dict(self.adam_segs['table'], lr=groups[0]['lr'], lr_ptr=lr_ptr)]
+        else:
+            segs = [dict(s, lr=groups[s['group']]['lr']) for k, s in self.adam_segs.items() if k != 'table']
+        if self._adam_total_tiles is None:
+            small = [s for k, s in self.adam_segs.items() if k != 'table']
+            self._adam_total_tiles = ops.adam_tile_count([dict(self.adam_segs['table'], lr=0.0)]) + ops.adam_tile_count([dict(s, lr=0.0) for s in small])
+        ops.adam_update_shared(segs, 0.9, 0.999, 1e-15, step, scale, inf, self.tick, self._adam_total_tiles)
+
+    def _table_update(self):
+        """The deferred half of an optimizer step: Adam on the table segment (the step's bookkeeping rides on its last block)."""
+        self._adam_shared('table', lr_ptr=self.lr_table_dev.data_ptr())
         self.lr_table_dev.copy_(self.lr_dev[:1])            # the update issued at the end of the CURRENT step uses the current rate
 
     def synchronize_parameters(self):
@@ -547,26 +559,15 @@ class NerfRunner:
             if not overlap and pending != 'deferred':       # this step's update is issued by the next step: keep this step's rate for it
                 self.lr_table_dev.copy_(self.lr_dev[:1])
 
-        step, scale, inf = self._adam_scalars()
-
         def fork():                                         # the table's gradient is complete: start its Adam pass now
             if overlap:
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    seg = dict(self.adam_segs['table'], lr=self.optimizer.param_groups[0]['lr'], lr_ptr=self.lr_dev[:1].data_ptr())
-                    ops.adam_update([seg], 0.9, 0.999, 1e-15, step, scale, inf)
+                    self._adam_shared('table', lr_ptr=self.lr_dev[:1].data_ptr())
 
         b = self._forward_backward(batch, t_rand=t_rand, before_fused=join, gather=gather, after_fused=fork)
-        groups = self.optimizer.param_groups
-        small = [dict(s, lr=groups[s['group']]['lr']) for k, s in self.adam_segs.items() if k != 'table']
-        ops.adam_update(small, 0.9, 0.999, 1e-15, step, scale, inf)
-        if overlap:
-            side.wait_stream(main)                          # the bookkeeping follows BOTH updates (they read step / scale / found_inf)
-            with torch.cuda.stream(side):
-                ops.adam_finish(0.9, 0.999, step, scale, inf, tick=self.tick)
-            self._table_pending = 'inflight'
-        else:
-            self._table_pending = 'deferred'
+        self._adam_shared('small')
+        self._table_pending = 'inflight' if overlap else 'deferred'
         return b
 
     def _graph_usable(self, t_rand):
@@ -843,7 +844,7 @@ class NerfRunner:
             shutil.copyfile(out_file, latest)
 
     def load_weights(self, ckpt_path):
-        self._table_pending = False                         # whatever was pending is overwritten by the checkpoint
+        self.synchronize_parameters()                       # a pending table update completes (and with it the step's bookkeeping counter) before the checkpoint overwrites everything
         ckpt = torch.load(ckpt_path, map_location=self.device, weights_only=False)
         self.models['model'].load_state_dict(ckpt['model'])            # copies INTO the flat-buffer views
         self.models['embed_fn'].load_state_dict(ckpt['embed_fn'])

@@ -162,6 +162,22 @@ def adam_update(segs, beta1, beta2, eps, step, scale_state=None, found_inf=None)
                                    _lib.ptr(found_inf), _lib.stream()), 'nof_adam_update')
 
 
+def adam_tile_count(segs):
+    """nof_adam_tile_count: thread blocks one update launch of `segs` takes (the unit nof_adam_update_shared counts in)."""
+    n = _lib.load().nof_adam_tile_count(_adam_segs(segs), len(segs))
+    if n < 0:
+        _lib.check(n, 'nof_adam_tile_count')
+    return n
+
+
+def adam_update_shared(segs, beta1, beta2, eps, step, scale_state, found_inf, tick, total_tiles):
+    """nof_adam_update_shared: like adam_update; the launch (of those sharing `total_tiles`) that retires last does the step's bookkeeping."""
+    _check_step_buf(step)
+    arr = _adam_segs(segs)
+    _lib.check(_lib.load().nof_adam_update_shared(arr, len(segs), float(beta1), float(beta2), float(eps), _lib.ptr(step), _lib.ptr(scale_state),
+                                                  _lib.ptr(found_inf), _lib.ptr(tick), int(total_tiles), _lib.stream()), 'nof_adam_update_shared')
+
+
 def adam_finish(beta1, beta2, step, scale_state=None, found_inf=None, tick=None):
     """nof_adam_finish: the bookkeeping of one optimizer step after all nof_adam_update launches of that step."""
     _check_step_buf(step)

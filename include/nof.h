@@ -251,6 +251,13 @@ int nof_adam_update(const NofAdamSeg* segs, int n_segs, float beta1, float beta2
                     const float* scale_state, const int32_t* found_inf, nof_stream_t stream);
 int nof_adam_finish(int32_t* step, float* scale_state, int32_t* found_inf, uint64_t* tick, float beta1, float beta2,
                     nof_stream_t stream);
+/* One optimizer step spread over SEVERAL launches that may run on different streams in any order (e.g. the table segment next to the
+ * pose backward, the small segments after it): each launch updates its segments like nof_adam_update, and the launch whose last block
+ * retires last does the bookkeeping of nof_adam_finish — no extra launch on the step's critical path. total_tiles = the sum of
+ * nof_adam_tile_count() over all launches of the step; every one of them passes the same value, `step` (not NULL) holds the counter. */
+int nof_adam_tile_count(const NofAdamSeg* segs, int n_segs);
+int nof_adam_update_shared(const NofAdamSeg* segs, int n_segs, float beta1, float beta2, float eps, int32_t* step,
+                           float* scale_state, int32_t* found_inf, uint64_t* tick, int total_tiles, nof_stream_t stream);
 
 /* SDF-only inference for mesh extraction (run_network_density, nerf_runner.py:1307-1347 with
  * NeRFSmall.forward_sdf nerf_helpers.py:296-302): x [P,3] in [-1,1] (clipped inside) -> sdf [P]. */
