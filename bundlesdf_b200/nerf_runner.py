@@ -247,6 +247,7 @@ class NerfRunner:
         self._done_ticket = torch.zeros(1, dtype=torch.int32, device=dev)   # CTA completion ticket of nof_step_prologue
         self.lr_table_dev = self.lr_dev[:1].clone()                         # learning rate of the pending table update (lags lr_dev by one step)
         self._graph = {}                                    # captured step graphs by (batch size, table update pending)
+        self._host = None                                   # staging state of train_steps(host_pool=...)
         self._eager_steps = 0
         segs = [dict(name='table', param=self.table.view(-1), grad=z(self.table).view(-1), exp_avg=z(self.table).view(-1),
                      exp_avg_sq=z(self.table).view(-1), shadow_f16=(self.table_f16.view(-1) if self.table_f16 is not None else None), group=0),
@@ -422,6 +423,7 @@ class NerfRunner:
         self.data_loader = DataLoader(rays=self.rays, batch_size=self.cfg['N_rand'])
         self._step_buf = None
         self._graph = {}                                    # captured step graphs by (batch size, table update pending)
+        self._host = None                                   # staging state of train_steps(host_pool=...)
 
     # ------------------------------------------------------------------ the hot path
     def _ensure_step_buffers(self, N):
@@ -532,7 +534,7 @@ class NerfRunner:
             torch.cuda.current_stream().wait_stream(self._table_stream)
         self._table_pending = False
 
-    def _step(self, batch, t_rand=None, gather=False, overlap=False):
+    def _step(self, batch, t_rand=None, gather=False, overlap=False, wait_before_fused=None, record_after_fused=None):
         """Forward, backward and optimizer of one step on the current stream (also what the CUDA graphs capture).
 
         cfg['defer_table_update']: the table's Adam pass (310 MB of HBM traffic at C2, the only part of the step that is bandwidth-bound)
@@ -542,11 +544,13 @@ class NerfRunner:
                          in the same stream order or the same CUDA graph, so the captured blocks use it for all but their last step.
           overlap=False  left to the NEXT step ('deferred'), which issues it first thing next to its own prologue / ray march: the only
                          placement that overlaps across a graph boundary (single-step graphs, last step of a block)."""
+        main = torch.cuda.current_stream()
         if not self._defer:
-            b = self._forward_backward(batch, t_rand=t_rand, gather=gather)
+            b = self._forward_backward(batch, t_rand=t_rand, gather=gather,
+                                       before_fused=(lambda: main.wait_event(wait_before_fused)) if wait_before_fused is not None else None,
+                                       after_fused=(lambda: record_after_fused.record(main)) if record_after_fused is not None else None)
             self._optimizer_step()
             return b
-        main = torch.cuda.current_stream()
         pending, side = self._table_pending, self._table_stream
         if pending == 'deferred':                           # fork: table update of the PREVIOUS step
             side.wait_stream(main)
@@ -554,12 +558,16 @@ class NerfRunner:
                 self._table_update()
 
         def join():                                         # the fused kernel is the first reader of the table
+            if wait_before_fused is not None:
+                main.wait_event(wait_before_fused)
             if pending:
                 main.wait_stream(side)
             if not overlap and pending != 'deferred':       # this step's update is issued by the next step: keep this step's rate for it
                 self.lr_table_dev.copy_(self.lr_dev[:1])
 
         def fork():                                         # the table's gradient is complete: start its Adam pass now
+            if record_after_fused is not None:
+                record_after_fused.record(main)
             if overlap:
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
@@ -635,11 +643,16 @@ class NerfRunner:
         if self.global_step % cfg['i_print'] == 0:
             logging.info(f'Iter: {self.global_step}, ' + ', '.join(f'{k}: {v:.7f}' for k, v in self.get_metrics().items()))
 
-    def train_steps(self, n):
+    def train_steps(self, n, host_pool=None):
         """`n` consecutive train steps (what train() loops over: draw a batch from the ray pool, train_loop, global_step += 1),
         with the host out of the loop: batches are gathered ON THE DEVICE at the data loader's cursor, and runs of
         cfg['graph_block_steps'] (default 10) steps that need no host action in between (lr schedule every 10 steps, checkpoints,
-        metric prints) replay as ONE CUDA graph. Same trajectory as calling train_loop(next(data_loader)) n times."""
+        metric prints) replay as ONE CUDA graph. Same trajectory as calling train_loop(next(data_loader)) n times.
+
+        host_pool: a pinned CPU copy of the ray pool [P,12] (the reference keeps its pool on the host, nerf_runner.py:431; also the way to
+        train on a pool that does not fit next to the model in HBM). Every step's batch is then gathered on the HOST, in the data loader's
+        order, and crosses PCIe inside the step's graph (one H2D copy node per step, running under the previous step's kernels); every
+        step's loss terms come back through a D2H node and are handed out by collect_host_losses()."""
         K = max(1, int(self.cfg.get('graph_block_steps', 10)))
         N = self.cfg['N_rand']
         dl = self.data_loader
@@ -651,28 +664,133 @@ class NerfRunner:
                 self._step(self._static_batch(N), gather=True)
                 k = 1
             else:
-                k = min(K, n - done)
-                for j in range(k - 1):                      # a block ends at the first step the host has to act after
-                    if self._host_action_after(self.global_step + j):
-                        k = j + 1
-                        break
+                k = self._block_len(self.global_step, min(K, n - done))
                 k = dl.reserve(k)
                 if k < K:
                     k = 1
-                key = ('blk', N, k, self._table_pending)
-                g = self._graph.get(key)
-                if g is None:
-                    self._static_batch(N)
-                    g = self._capture(key, k, gather=True)  # capturing does not execute: replay below runs these k steps
-                g['graph'].replay()
+                if host_pool is not None:
+                    self._replay_host_block(k, host_pool)
+                else:
+                    key = ('blk', N, k, self._table_pending)
+                    g = self._graph.get(key)
+                    if g is None:
+                        self._static_batch(N)
+                        g = self._capture(key, k, gather=True)  # capturing does not execute: replay below runs these k steps
+                    g['graph'].replay()
+                    self._step_buf = g['buf']
                 if self._defer:
                     self._table_pending = 'deferred'
-                self._step_buf = g['buf']
             dl.consumed(k)
             self.global_step += k - 1                       # the host acts once, after the block's last step
             self._after_step()
             self.global_step += 1
             done += k
+        if host_pool is not None and self._host is not None:
+            self._prefetch_host_block(host_pool)
+
+    def _block_len(self, gstep, k):
+        for j in range(k - 1):                              # a block ends at the first step the host has to act after
+            if self._host_action_after(gstep + j):
+                return j + 1
+        return k
+
+    # ---- host-resident ray pool (train_steps(host_pool=...))
+    def _host_state(self, K, N):
+        h = self._host
+        if h is None or h['K'] != K or h['N'] != N:
+            h = dict(K=K, N=N, slot=0, stage=[torch.empty(K, N, 12).pin_memory() for _ in range(2)],
+                     loss=[torch.zeros(K, 8).pin_memory() for _ in range(2)], dev=[torch.empty(N, 12, device=self.device) for _ in range(2)],
+                     ev=[None, None], meta=[None, None], staged=[None, None], up=torch.cuda.Stream(), down=torch.cuda.Stream(), out=[])
+            self._host = h
+        return h
+
+    def _stage_host(self, h, slot, pos, k, host_pool):
+        """Gather batches [pos, pos + k*N) of the epoch permutation from the pinned pool into staging slot `slot` (one host thread)."""
+        N = h['N']
+        ids = self.data_loader.ids[pos:pos + k * N].numpy()
+        np.take(host_pool.numpy(), ids, axis=0, out=h['stage'][slot].numpy()[:k].reshape(k * N, 12))
+        h['staged'][slot] = (pos, k, id(self.data_loader.ids))
+
+    def _drain_host_slot(self, h, slot):
+        if h['ev'][slot] is not None:
+            h['ev'][slot].synchronize()
+            first, k = h['meta'][slot]
+            h['out'].append((first, h['loss'][slot][:k].clone().numpy()))
+            h['ev'][slot] = None
+
+    def _replay_host_block(self, k, host_pool):
+        N = self.cfg['N_rand']
+        h = self._host_state(max(1, int(self.cfg.get('graph_block_steps', 10))), N)
+        slot = h['slot']
+        h['slot'] ^= 1
+        self._drain_host_slot(h, slot)                      # the block that used this staging slot two blocks ago is done: its losses are read
+        pos = self.data_loader.pos
+        if h['staged'][slot] != (pos, k, id(self.data_loader.ids)):
+            self._stage_host(h, slot, pos, k, host_pool)
+        key = ('hblk', N, k, self._table_pending, slot)
+        g = self._graph.get(key)
+        if g is None:
+            g = self._capture_host(key, k, h, slot)
+        g['graph'].replay()
+        ev = torch.cuda.Event()
+        ev.record()
+        h['ev'][slot], h['meta'][slot], h['staged'][slot] = ev, (self.global_step, k), None
+        self._step_buf = g['buf']
+
+    def _prefetch_host_block(self, host_pool):
+        """Stage the NEXT block's batches while the block just launched runs (the caller usually comes back for more steps)."""
+        h, dl = self._host, self.data_loader
+        K = h['K']
+        if self._block_len(self.global_step, K) < K or dl.batches_left() < K:
+            return
+        slot = h['slot']
+        self._drain_host_slot(h, slot)
+        self._stage_host(h, slot, dl.pos, K, host_pool)
+
+    def collect_host_losses(self):
+        """Loss terms [n,8] (include/nof.h: losses) of every step run through train_steps(host_pool=...) since the last call, in step
+        order. Waits for the blocks still in flight."""
+        h = self._host
+        if h is None:
+            return np.zeros((0, 8), dtype=np.float32)
+        for slot in (0, 1):
+            self._drain_host_slot(h, slot)
+        out = sorted(h['out'], key=lambda t: t[0])
+        h['out'] = []
+        return np.concatenate([o[1] for o in out], 0) if out else np.zeros((0, 8), dtype=np.float32)
+
+    def _capture_host(self, key, n_steps, h, slot):
+        """Like _capture, but every step's batch arrives by an H2D copy node from the pinned staging slot (into one of two device buffers,
+        under the previous step's kernels) and every step's losses leave by a D2H node right after its fused kernel."""
+        self._ensure_step_buffers(h['N'])
+        stage, lossh, dev, up, down = h['stage'][slot], h['loss'][slot], h['dev'], h['up'], h['down']
+        cap = torch.cuda.Stream(priority=-1 if self._defer else 0)
+        cap.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cap):
+            main = torch.cuda.current_stream()
+            up.wait_stream(main)                            # uploads and downloads on their own streams: an upload queued behind a download
+            down.wait_stream(main)                          # would wait for that step's fused kernel and land on the next step's critical path
+            ev_up = [torch.cuda.Event() for _ in range(n_steps)]
+            ev_fused = [torch.cuda.Event() for _ in range(n_steps)]
+            ev_loss = [torch.cuda.Event() for _ in range(n_steps)]
+            for i in range(n_steps):
+                with torch.cuda.stream(up):
+                    if i >= 2:
+                        up.wait_event(ev_fused[i - 2])       # the ray march and the fused kernel of step i-2 have read this buffer
+                    dev[i % 2].copy_(stage[i], non_blocking=True)
+                    ev_up[i].record(up)
+                main.wait_event(ev_up[i])
+                self._step(dev[i % 2], gather=False, overlap=(i + 1 < n_steps), wait_before_fused=(ev_loss[i - 1] if i else None),
+                           record_after_fused=ev_fused[i])
+                with torch.cuda.stream(down):
+                    down.wait_event(ev_fused[i])
+                    lossh[i].copy_(self._step_buf['losses'], non_blocking=True)   # before the next step's operand pack zeroes them
+                    ev_loss[i].record(down)
+            main.wait_stream(up)
+            main.wait_stream(down)
+        self._graph[key] = g = dict(graph=graph, batch=dev[0], buf=self._step_buf)
+        return g
 
     def train_loop(self, batch, t_rand=None):
         """One train step (reference nerf_runner.py:679-852): forward, losses, backward, optimizer step, lr schedule."""
@@ -885,3 +1003,4 @@ class NerfRunner:
         self.global_step = int(ckpt.get('global_step', 0))
         self._step_buf = None
         self._graph = {}                                    # captured step graphs by (batch size, table update pending)
+        self._host = None                                   # staging state of train_steps(host_pool=...)

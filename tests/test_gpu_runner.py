@@ -250,6 +250,38 @@ def test_train_steps_blocks_match_per_step_loop():
     assert rel(rb.table, ra.table) < 0.2 and rel(rb.mlp_flat, ra.mlp_flat) < 0.1
 
 
+@pytest.mark.parametrize('defer', [False, True])
+def test_train_steps_from_a_host_pool_match_the_device_pool(defer):
+    """train_steps(n, host_pool=pinned copy of the ray pool): batches gathered on the host in the loader's order and uploaded by one H2D node
+    per step inside the block graph, losses returned by one D2H node per step — same batches, same ticks, same trajectory as the
+    device-resident pool (within the noise of the atomics), and one loss row per step that ran through a graph."""
+    from bundlesdf_b200.nerf_runner import set_seed
+    ra, _ = _runner(True, n_frames=4, N=256, defer_table_update=defer)
+    rb, _ = _runner(True, n_frames=4, N=256, defer_table_update=defer)
+    n = 53                                                  # eager steps, singles, 10-step blocks, a tail; crosses an epoch boundary
+    set_seed(0)
+    ra.train_steps(n)
+    set_seed(0)
+    pool = rb.rays.cpu().pin_memory()
+    rb.train_steps(31, host_pool=pool)
+    first = rb.collect_host_losses()
+    rb.train_steps(n - 31, host_pool=pool)
+    rest = rb.collect_host_losses()
+    ra.synchronize_parameters(); rb.synchronize_parameters()
+    assert rb.global_step == ra.global_step == n
+    assert rb.adam_step_count.item() == ra.adam_step_count.item()
+    assert rb.march_tick.item() == ra.march_tick.item() == n
+    assert rb.data_loader.pos == ra.data_loader.pos
+    assert any(k[0] == 'hblk' and k[2] == 10 for k in rb._graph), list(rb._graph)
+    rows = np.concatenate([first, rest], 0)
+    assert len(rows) == n - 2 and np.isfinite(rows).all()   # the first two steps run eagerly (buffer allocation), the rest through graphs
+    la, lb = ra.get_metrics(), rb.get_metrics()
+    assert lb['loss'] == pytest.approx(la['loss'], rel=0.05)
+    assert rows[-1, 0] == pytest.approx(float(rb._step_buf['losses'][0]), rel=1e-6)      # the last row IS the last step's loss
+    rel = lambda a, w: float((a - w).norm() / w.norm())
+    assert rel(rb.table, ra.table) < 0.2 and rel(rb.mlp_flat, ra.mlp_flat) < 0.1
+
+
 def test_pose_regulariser_follows_the_loss_scale():
     """pose_reg_weight > 0 under AMP: the regulariser's gradient is added to the (loss-scaled) pose gradient buffer multiplied by the
     loss scale, so that the single unscale inside nof_adam_step recovers d/dpose [pose_reg_weight * ||data[1:]||] (nerf_runner.py:748-758)."""
