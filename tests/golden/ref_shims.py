@@ -61,6 +61,11 @@ def import_reference(ref_dir=None, mycuda_common=None, mycuda_gridencoder=None):
     if ref_dir not in sys.path:
         sys.path.insert(0, ref_dir)
     import importlib
+    if mycuda_common is not None or mycuda_gridencoder is not None:
+        # an earlier import of the reference in this process WITHOUT its extensions (the CPU-side golden tests) left modules whose
+        # `from mycuda import common` failed silently: import them afresh now that the extensions are there
+        for name in ('Utils', 'nerf_helpers', 'nerf_runner'):
+            sys.modules.pop(name, None)
     Utils = importlib.import_module('Utils')
     nerf_helpers = importlib.import_module('nerf_helpers')
     nerf_runner = importlib.import_module('nerf_runner')
