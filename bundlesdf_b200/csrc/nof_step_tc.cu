@@ -110,9 +110,18 @@ __device__ __forceinline__ void flush_tmem(uint32_t tq, int col0, int warp, int 
     TmemLd<8>::ld(tq + col0 + c, v);                       // warp-collective: lanes >= 16 read unused TMEM lanes
     if (lane < 16) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float* dst = addr(row, c + j);
-        if (dst && v[j] != 0.f) red_add(dst, v[j]);
+      for (int j = 0; j < 8; j += 4) {
+        float* d0 = addr(row, c + j);
+        float* d3 = addr(row, c + j + 3);
+        if (d0 && d3 == d0 + 3 && (reinterpret_cast<uintptr_t>(d0) & 15u) == 0u) {          // four columns of a row-major weight: one 16-byte reduction
+          if (v[j] != 0.f || v[j + 1] != 0.f || v[j + 2] != 0.f || v[j + 3] != 0.f) red_add_v4(d0, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float* dst = addr(row, c + j + k);
+            if (dst && v[j + k] != 0.f) red_add(dst, v[j + k]);
+          }
+        }
       }
     }
   }
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
   const int rl = pt / Sp, sidx = pt - rl * Sp;
   const int l_beg = half ? (L + 1) >> 1 : 0, l_end = half ? L : (L + 1) >> 1;
   const bool owner = half == 0;
-  __half2* Jslot = reinterpret_cast<__half2*>(a.jws) + (size_t)blockIdx.x * (MAX_L * 3) * PT;
+  uint4* Jslot = reinterpret_cast<uint4*>(a.jws) + (size_t)blockIdx.x * MAX_L * PT;      // [level][point]: d enc / d u as 3 x half2 (+ pad) = one 16-byte access
   const int g8 = lane >> 2, t4 = lane & 3;
   const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);     // TMEM address of this warp's lane quadrant
 
@@ -329,8 +338,7 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
 #else
           gather_level<true, true>(a.p.table_f16, lv, l, u, enc, J);
 #endif
-#pragma unroll
-          for (int d = 0; d < 3; ++d) Jslot[(size_t)(l * 3 + d) * PT + pt] = __floats2half2_rn(J[d][0], J[d][1]);
+          Jslot[(size_t)l * PT + pt] = make_uint4(pack_h2(J[0][0], J[0][1]), pack_h2(J[1][0], J[1][1]), pack_h2(J[2][0], J[2][1]), 0u);
         } else {
           gather_level<true, false>(a.p.table_f16, lv, l, u, enc, J);
         }
@@ -670,9 +678,11 @@ __global__ void __launch_bounds__(NT, 2) step_tc_kernel(const StepArgs a) {
               live = (g0 != 0.f || g1 != 0.f);
               if (a.p.need_pose_grad && live) {
                 float gx[3];
+                const uint4 jv = Jslot[(size_t)l * PT + q];
+                const uint32_t jw[3] = {jv.x, jv.y, jv.z};
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                  const float2 jj = __half22float2(Jslot[(size_t)(l * 3 + d) * PT + q]);
+                  const float2 jj = __half22float2(*reinterpret_cast<const __half2*>(&jw[d]));
                   gx[d] = 0.5f * fmaf(g0, jj.x, g1 * jj.y);
                   st[d] += gx[d];
                   st[3 + d] = fmaf(gx[d], zq, st[3 + d]);
