@@ -18,13 +18,13 @@ _vp, _i32, _u32, _u64, _f32, _sz, _i64 = C.c_void_p, C.c_int32, C.c_uint32, C.c_
 class NofMarchCfg(C.Structure):
     _fields_ = [('N', _i32), ('ray_dim', _i32), ('S_occ', _i32), ('S_depth', _i32), ('level', _i32), ('I_max', _i32),
                 ('trunc', _f32), ('near_sc', _f32), ('far_sc', _f32), ('neg_trunc_ratio', _f32), ('perturb', _i32),
-                ('seed', _u64), ('offset', _u64), ('offset_ptr', _vp)]
+                ('seed', _u64), ('offset', _u64), ('offset_ptr', _vp), ('trunc_ptr', _vp)]
 
 
 class NofPrologue(C.Structure):
     _fields_ = [('pool', _vp), ('ids', _vp), ('n_ids', _i64), ('batch', _vp), ('N', _i32), ('ray_dim', _i32), ('cursor', _vp),
                 ('pose_data', _vp), ('c2w', _vp), ('tf', _vp), ('F', _i32), ('max_trans', _f32), ('max_rot_deg', _f32),
-                ('tick', _vp), ('done', _vp)]
+                ('tick', _vp), ('done', _vp), ('trunc_table', _vp), ('trunc_len', _i32), ('gstep', _vp), ('trunc_out', _vp)]
 
 
 class NofStep(C.Structure):
@@ -36,7 +36,7 @@ class NofStep(C.Structure):
                 ('fs_rgb_weight', _f32), ('first_frame_weight', _f32),
                 ('loss_scale', _vp), ('need_pose_grad', _i32),
                 ('grad_table', _vp), ('grad_mlp', _vp), ('grad_tf', _vp), ('grad_feat', _vp), ('losses', _vp), ('found_inf', _vp),
-                ('rgb_map', _vp), ('raw', _vp), ('valid_samples', _vp), ('weights', _vp), ('workspace', _vp), ('eikonal_weight', _f32)]
+                ('rgb_map', _vp), ('raw', _vp), ('valid_samples', _vp), ('weights', _vp), ('workspace', _vp), ('eikonal_weight', _f32), ('trunc_ptr', _vp)]
 
 
 class NofAdamSeg(C.Structure):

@@ -180,6 +180,11 @@ __global__ void __launch_bounds__(256) step_prologue_kernel(const NofPrologue p)
       *p.done = 0;
       if (p.pool && p.cursor) *p.cursor = base + p.N;
       if (p.tick) *p.tick += 1ull;
+      if (p.gstep) {
+        const long long g = *p.gstep;
+        if (p.trunc_table && p.trunc_out && p.trunc_len > 0) *p.trunc_out = p.trunc_table[g < 0 ? 0 : (g >= p.trunc_len ? p.trunc_len - 1 : g)];
+        *p.gstep = g + 1;
+      }
     }
   }
 }
@@ -236,7 +241,8 @@ extern "C" int nof_pose_forward(const float* pose_data, const float* c2w, float*
 extern "C" int nof_step_prologue(const NofPrologue* p, nof_stream_t stream) {
   NOF_REQUIRE(p && p->c2w && p->tf && p->F >= 1, "nof_step_prologue: null pose pointers or F < 1");
   NOF_REQUIRE(!p->pool || (p->ids && p->batch && p->N >= 1 && p->ray_dim >= 1 && p->n_ids >= p->N), "nof_step_prologue: bad gather arguments");
-  NOF_REQUIRE(p->done || !(p->cursor || p->tick), "nof_step_prologue: counters need the `done` ticket");
+  NOF_REQUIRE(p->done || !(p->cursor || p->tick || p->gstep), "nof_step_prologue: counters need the `done` ticket");
+  NOF_REQUIRE(!p->trunc_out || (p->trunc_table && p->gstep && p->trunc_len >= 1), "nof_step_prologue: trunc_out needs trunc_table, trunc_len and gstep");
   const int work = std::max(p->pool ? p->N * p->ray_dim : 0, p->F);
   step_prologue_kernel<<<std::max(1, std::min(div_up(work, 256), 128)), 256, 0, as_stream(stream)>>>(*p);
   return check_launch("step_prologue_kernel");

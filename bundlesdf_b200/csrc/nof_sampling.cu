@@ -288,7 +288,8 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg
     // ---- z intervals: t -> z (nerf_runner.py:987-990), clip to depth+trunc for valid-depth rays (:992-999)
     const float absz = fabsf(uz);
     const bool valid_depth = (depth >= cfg.near_sc) && (depth <= cfg.far_sc);
-    const float zmax = __fadd_rn(depth, cfg.trunc);
+    const float trunc = cfg.trunc_ptr ? __ldg(cfg.trunc_ptr) : cfg.trunc;     // annealed truncation: a device scalar (NofPrologue.trunc_out)
+    const float zmax = __fadd_rn(depth, trunc);
     for (int k = lane; k < I; k += 32) {
       float a = 0.f, b = 0.f;
       if (k < count) {
@@ -315,8 +316,8 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) ray_march_kernel(NofMarchCfg
     float total2 = 0.f;
     if (cfg.S_depth > 0 && !valid_depth)
       for (int k = 0; k < count; ++k) total2 = __fadd_rn(total2, __fsub_rn(io_t[2 * k + 1], io_t[2 * k]));
-    const float nd = __fsub_rn(depth, cfg.trunc);
-    const float fd = __fadd_rn(depth, __fmul_rn(cfg.trunc, cfg.neg_trunc_ratio));
+    const float nd = __fsub_rn(depth, trunc);
+    const float fd = __fadd_rn(depth, __fmul_rn(trunc, cfg.neg_trunc_ratio));
     bool err = false;
     float* zrow = z_vals + (size_t)r * S;
     const bool has_any = io_z[0] != 0.f;       // common.cu:54: rays without intervals keep z = 0

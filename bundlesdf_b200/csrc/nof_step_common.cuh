@@ -171,13 +171,17 @@ __device__ __forceinline__ void setup_ray(RayS& rs, const StepArgs& a, int ray) 
   sh3(rs.dw, rs.views + a.p.ff);
 }
 
+// Truncation of this step: a device scalar when the schedule anneals it (NofStep.trunc_ptr), else the launch constant.
+__device__ __forceinline__ float step_trunc(const StepArgs& a) { return a.p.trunc_ptr ? __ldg(a.p.trunc_ptr) : a.p.trunc; }
+
 // Raw (un-normalised) compositing weight, nerf_runner.py:1152-1159.
 __device__ __forceinline__ float raw_weight(const StepArgs& a, float z, float depth) {
   if (depth > a.p.far_sc) return 0.f;
-  const float s = (depth - z) / a.p.trunc;
+  const float trunc = step_trunc(a);
+  const float s = (depth - z) / trunc;
   float w = sigmoidf_(s * a.p.sdf_lambda) * sigmoidf_(-s * a.p.sdf_lambda);
   const float dz = z - depth;
-  const bool m = (dz <= a.p.trunc * a.p.neg_trunc_ratio) && (dz >= -a.p.trunc);
+  const bool m = (dz <= trunc * a.p.neg_trunc_ratio) && (dz >= -trunc);
   return m ? w : 0.f;
 }
 
@@ -353,7 +357,7 @@ __device__ __forceinline__ void loss_seeds(const StepArgs& a, const RayS& rs, co
     d_out[c] = dmap * w * rgb_s[c] * (1.f - rgb_s[c]);
   }
   const float sdf = out[3];
-  const float tr = a.p.trunc;
+  const float tr = step_trunc(a);
   const bool front = z < depth - tr;
   const bool back = z > depth + tr * a.p.neg_trunc_ratio;
   const bool valid_depth = (depth >= a.p.near_sc) && (depth <= a.p.far_sc);

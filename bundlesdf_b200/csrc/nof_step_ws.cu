@@ -182,7 +182,7 @@ __device__ __forceinline__ void loss_seeds_w(const StepArgs& a, float depth, con
     d_out[c] = dmap * w * rgb_s[c] * (1.f - rgb_s[c]);
   }
   const float sdf = out[3];
-  const float tr = a.p.trunc;
+  const float tr = step_trunc(a);
   const bool front = z < depth - tr;
   const bool back = z > depth + tr * a.p.neg_trunc_ratio;
   const bool valid_depth = (depth >= a.p.near_sc) && (depth <= a.p.far_sc);

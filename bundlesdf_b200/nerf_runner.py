@@ -248,6 +248,7 @@ class NerfRunner:
         self.lr_table_dev = self.lr_dev[:1].clone()                         # learning rate of the pending table update (lags lr_dev by one step)
         self._graph = {}                                    # captured step graphs by (batch size, table update pending)
         self._host = None                                   # staging state of train_steps(host_pool=...)
+        self._trunc_dev = None                              # device-side truncation schedule (trunc_decay_type linear|exp)
         self._eager_steps = 0
         segs = [dict(name='table', param=self.table.view(-1), grad=z(self.table).view(-1), exp_avg=z(self.table).view(-1),
                      exp_avg_sq=z(self.table).view(-1), shadow_f16=(self.table_f16.view(-1) if self.table_f16 is not None else None), group=0),
@@ -287,17 +288,38 @@ class NerfRunner:
             g['lr'] = self.param_groups_init[i]['lr'] * (self.cfg['decay_rate'] ** (float(self.global_step) / self.N_iters))
         self.lr_dev.copy_(torch.tensor([g['lr'] for g in self.optimizer.param_groups], dtype=torch.float32))
 
-    def get_truncation(self):
-        """nerf_runner.py:663-676."""
+    def get_truncation(self, step=None):
+        """nerf_runner.py:663-676 (at `step`, default the current global_step)."""
         cfg = self.cfg
+        g = self.global_step if step is None else step
         if cfg['trunc_decay_type'] == 'linear':
-            t = cfg['trunc_start'] - (cfg['trunc_start'] - cfg['trunc']) * float(self.global_step) / cfg['n_step']
+            t = cfg['trunc_start'] - (cfg['trunc_start'] - cfg['trunc']) * float(g) / cfg['n_step']
         elif cfg['trunc_decay_type'] == 'exp':
             lamb = np.log(cfg['trunc'] / cfg['trunc_start']) / (cfg['n_step'] / 4)
-            t = max(cfg['trunc_start'] * np.exp(self.global_step * lamb), cfg['trunc'])
+            t = max(cfg['trunc_start'] * np.exp(g * lamb), cfg['trunc'])
         else:
             t = cfg['trunc']
         return t * cfg['sc_factor']
+
+    def _trunc_schedule(self):
+        """Annealed truncation (trunc_decay_type linear|exp) as device state, so that the captured steps keep static launch arguments: the
+        per-step values of get_truncation() in a table, the step index in a device counter that nof_step_prologue advances, and the
+        scalar it writes for the ray march and the fused kernel of the same step. None for the constant schedule."""
+        if self.cfg.get('trunc_decay_type', '') == '':
+            return None
+        ts = self._trunc_dev
+        n = int(self.cfg['n_step']) + 2
+        if ts is None or ts['n'] != n:
+            table = torch.tensor([self.get_truncation(g) for g in range(n)], dtype=torch.float32, device=self.device)
+            ts = self._trunc_dev = dict(n=n, table=table, gstep=torch.full((1,), int(self.global_step), dtype=torch.int64, device=self.device),
+                                        out=torch.full((1,), float(self.get_truncation()), device=self.device))
+        return ts
+
+    def _sync_trunc_step(self):
+        """Before launching one step or one block of steps: the device step counter := global_step (the prologue of every step advances it)."""
+        ts = self._trunc_schedule()
+        if ts is not None:
+            ts['gstep'].fill_(int(self.global_step))
 
     # ------------------------------------------------------------------ occupancy / ray pool (upstream of the hot path)
     def build_octree(self):
@@ -424,6 +446,7 @@ class NerfRunner:
         self._step_buf = None
         self._graph = {}                                    # captured step graphs by (batch size, table update pending)
         self._host = None                                   # staging state of train_steps(host_pool=...)
+        self._trunc_dev = None                              # device-side truncation schedule (trunc_decay_type linear|exp)
 
     # ------------------------------------------------------------------ the hot path
     def _ensure_step_buffers(self, N):
@@ -467,14 +490,17 @@ class NerfRunner:
         pa = self.models['pose_array']
         trunc = self.get_truncation()
         dl = self.data_loader
+        ts = self._trunc_schedule()
+        tp = ts['out'] if ts is not None else None
         ops.step_prologue(pa.data.data if pa is not None else None, self.c2w_array, b['tf'], cfg['max_trans'] * sc, cfg['max_rot'],
                           pool=(self.rays if gather else None), ids=(dl.ids_dev if gather else None), batch=batch,
-                          cursor=(dl.cursor_dev if gather else None), tick=self.march_tick, done=self._done_ticket)
+                          cursor=(dl.cursor_dev if gather else None), tick=self.march_tick, done=self._done_ticket,
+                          trunc_table=(ts['table'] if ts else None), gstep=(ts['gstep'] if ts else None), trunc_out=tp)
         ops.ray_march(batch, b['tf'], self.octree_m.occ_bits, self.octree_m.level, cfg['N_samples'], cfg['N_samples_around_depth'], trunc,
                       cfg['near'] * sc, cfg['far'] * sc, cfg['neg_trunc_ratio'], t_rand=t_rand, perturb=bool(cfg.get('perturb', 1)),
-                      seed=0x5DEECE66D, offset=0, offset_ptr=self.march_tick, z_vals=b['z_vals'], err_flag=b['march_err'])
+                      seed=0x5DEECE66D, offset=0, offset_ptr=self.march_tick, z_vals=b['z_vals'], err_flag=b['march_err'], trunc_ptr=tp)
         ops.fill_step_cfg(sb, cfg, trunc)
-        sb.set(rays=batch)
+        sb.set(rays=batch, trunc_ptr=tp)
         for k in ('rgb_map', 'raw', 'valid_samples', 'weights'):
             sb.set(**{k: (taps.get(k) if taps else None)})
         if before_fused is not None:
@@ -579,7 +605,7 @@ class NerfRunner:
         return b
 
     def _graph_usable(self, t_rand):
-        return (t_rand is None and bool(self.cfg.get('use_cuda_graph', True)) and self.cfg.get('trunc_decay_type', '') == '')
+        return t_rand is None and bool(self.cfg.get('use_cuda_graph', True))
 
     def _static_batch(self, N):
         if getattr(self, '_batch_static', None) is None or self._batch_static.shape[0] != N:
@@ -661,6 +687,7 @@ class NerfRunner:
             if not self._graph_usable(None) or self._eager_steps < 2:
                 self._eager_steps += 1
                 dl.reserve(1)
+                self._sync_trunc_step()
                 self._step(self._static_batch(N), gather=True)
                 k = 1
             else:
@@ -668,6 +695,7 @@ class NerfRunner:
                 k = dl.reserve(k)
                 if k < K:
                     k = 1
+                self._sync_trunc_step()
                 if host_pool is not None:
                     self._replay_host_block(k, host_pool)
                 else:
@@ -794,6 +822,7 @@ class NerfRunner:
 
     def train_loop(self, batch, t_rand=None):
         """One train step (reference nerf_runner.py:679-852): forward, losses, backward, optimizer step, lr schedule."""
+        self._sync_trunc_step()
         if self._graph_usable(t_rand):
             b = self._step_graphed(batch)
         else:
@@ -1004,3 +1033,4 @@ class NerfRunner:
         self._step_buf = None
         self._graph = {}                                    # captured step graphs by (batch size, table update pending)
         self._host = None                                   # staging state of train_steps(host_pool=...)
+        self._trunc_dev = None                              # device-side truncation schedule (trunc_decay_type linear|exp)

@@ -60,13 +60,15 @@ def pose_backward(pose_data, c2w, grad_tf, grad_pose, max_trans, max_rot_deg, lo
     return grad_pose
 
 
-def step_prologue(pose_data, c2w, tf, max_trans, max_rot_deg, pool=None, ids=None, batch=None, cursor=None, tick=None, done=None):
+def step_prologue(pose_data, c2w, tf, max_trans, max_rot_deg, pool=None, ids=None, batch=None, cursor=None, tick=None, done=None,
+                  trunc_table=None, gstep=None, trunc_out=None):
     """nof_step_prologue: [batch gather at the device cursor] + pose correction of all frames + counter bumps, one launch."""
     lib = _lib.load()
     F = c2w.shape[0]
     p = NofPrologue(_lib.ptr(pool), _lib.ptr(ids), int(ids.shape[0]) if ids is not None else 0, _lib.ptr(batch),
                     int(batch.shape[0]) if batch is not None else 0, int(batch.shape[1]) if batch is not None else 0, _lib.ptr(cursor),
-                    _lib.ptr(pose_data), _lib.ptr(c2w), _lib.ptr(tf), F, float(max_trans), float(max_rot_deg), _lib.ptr(tick), _lib.ptr(done))
+                    _lib.ptr(pose_data), _lib.ptr(c2w), _lib.ptr(tf), F, float(max_trans), float(max_rot_deg), _lib.ptr(tick), _lib.ptr(done),
+                    _lib.ptr(trunc_table), int(trunc_table.shape[0]) if trunc_table is not None else 0, _lib.ptr(gstep), _lib.ptr(trunc_out))
     _lib.check(lib.nof_step_prologue(C.byref(p), _lib.stream()), 'nof_step_prologue')
     return tf
 
@@ -80,7 +82,7 @@ def gather_rays(pool, ids, out=None):
 
 
 def ray_march(rays, tf, occ_bits, level, S_occ, S_depth, trunc, near_sc, far_sc, neg_trunc_ratio, t_rand=None, perturb=True,
-              seed=0, offset=0, I_max=None, z_vals=None, want_intervals=False, err_flag=None, offset_ptr=None):
+              seed=0, offset=0, I_max=None, z_vals=None, want_intervals=False, err_flag=None, offset_ptr=None, trunc_ptr=None):
     lib = _lib.load()
     N, D = rays.shape
     if I_max is None:
@@ -90,7 +92,7 @@ def ray_march(rays, tf, occ_bits, level, S_occ, S_depth, trunc, near_sc, far_sc,
         z_vals = torch.empty(N, S, device=rays.device, dtype=torch.float32)
     inter = torch.empty(N, I_max, 2, device=rays.device, dtype=torch.float32) if want_intervals else None
     cfg = NofMarchCfg(N, D, S_occ, S_depth, level, I_max, float(trunc), float(near_sc), float(far_sc), float(neg_trunc_ratio),
-                      int(bool(perturb)), int(seed), int(offset), _lib.ptr(offset_ptr))
+                      int(bool(perturb)), int(seed), int(offset), _lib.ptr(offset_ptr), _lib.ptr(trunc_ptr))
     _lib.check(lib.nof_ray_march(C.byref(cfg), _lib.ptr(rays), _lib.ptr(tf), _lib.ptr(occ_bits), _lib.ptr(t_rand), _lib.ptr(z_vals),
                                  _lib.ptr(inter), _lib.ptr(err_flag), _lib.stream()), 'nof_ray_march')
     return (z_vals, inter) if want_intervals else z_vals

@@ -125,6 +125,13 @@ typedef struct {
   float max_trans, max_rot_deg;
   uint64_t* tick;           /* optional device counter, +1 per call (NofMarchCfg.offset_ptr: the sampler's RNG stream position) */
   int32_t* done;            /* device int32, zero-initialised: CTA completion ticket (required when cursor or tick is given) */
+  /* truncation schedule on the device (cfg trunc_decay_type linear|exp, nerf_runner.py:663-676) so that the annealed truncation does not
+   * force one launch sequence per step: trunc_out[0] = trunc_table[min(*gstep, trunc_len-1)], then *gstep += 1 (by the last block).
+   * trunc_out is what NofMarchCfg.trunc_ptr / NofStep.trunc_ptr of the same step point to. All four NULL/0: constant truncation. */
+  const float* trunc_table; /* [trunc_len] device floats: truncation (normalised units) of step 0, 1, ... */
+  int32_t trunc_len;
+  int64_t* gstep;           /* device int64: the step index this launch belongs to */
+  float* trunc_out;         /* device float */
 } NofPrologue;
 int nof_step_prologue(const NofPrologue* p, nof_stream_t stream);
 
@@ -141,6 +148,7 @@ typedef struct {
   int perturb;          /* 1: stratified jitter */
   uint64_t seed, offset;/* Philox counter RNG (used when t_rand == NULL && perturb) */
   const uint64_t* offset_ptr; /* optional DEVICE counter added to `offset` (keeps the launch arguments static under CUDA graphs) */
+  const float* trunc_ptr;     /* optional DEVICE scalar overriding `trunc` (NofPrologue.trunc_out) */
 } NofMarchCfg;
 
 /* Replaces OctreeManager.ray_trace (Utils.py:443-475: kaolin unbatched_raytrace + unique_consecutive +
@@ -207,6 +215,7 @@ typedef struct {
    * cannot run it: it renders with get_normals=False, :686): eikonal_weight * mean over {sdf < 1} of (|d sdf / d x| - 1)^2, x detached.
    * > 0 needs amp == 1 and S <= 256 (built in the mma.sync tile kernel); the value of the term lands in losses[7]. */
   float eikonal_weight;
+  const float* trunc_ptr;       /* optional DEVICE scalar overriding `trunc` (NofPrologue.trunc_out): annealed truncation under CUDA graphs */
 } NofStep;
 
 size_t nof_step_workspace_bytes(const NofStep* p);

@@ -282,6 +282,55 @@ def test_train_steps_from_a_host_pool_match_the_device_pool(defer):
     assert rel(rb.table, ra.table) < 0.2 and rel(rb.mlp_flat, ra.mlp_flat) < 0.1
 
 
+@pytest.mark.parametrize('decay', ['linear', 'exp'])
+def test_annealed_truncation_runs_inside_the_graph_blocks(decay):
+    """trunc_decay_type linear | exp (nerf_runner.py:663-676): the per-step truncation lives in a device table indexed by a device step
+    counter (nof_step_prologue), so annealing no longer forces one launch sequence per step. Checked: the scalar the kernels read equals
+    get_truncation(step) after every stretch; one fused step in the middle of the schedule matches the oracle evaluated at that truncation; the blocks and the
+    per-step loop walk the same trajectory."""
+    from bundlesdf_b200.nerf_runner import set_seed
+    over = dict(trunc_decay_type=decay, trunc_start=0.03, trunc=0.01)
+    ra, _ = _runner(True, n_frames=4, N=256, **over)
+    rb, _ = _runner(True, n_frames=4, N=256, **over)
+    assert ra.get_truncation(0) > 2.5 * ra.get_truncation(60)
+    n = 41
+    set_seed(0)
+    for _ in range(n):
+        ra.train_loop(next(ra.data_loader))
+        ra.global_step += 1
+    set_seed(0)
+    rb.train_steps(n)
+    assert any(k[0] == 'blk' and k[2] == 10 for k in rb._graph), list(rb._graph)
+    for r in (ra, rb):
+        ts = r._trunc_schedule()
+        assert int(ts['gstep'].item()) == n
+        assert float(ts['out'].item()) == np.float32(r.get_truncation(n - 1))        # what the last step's kernels read
+    la, lb = ra.get_metrics(), rb.get_metrics()
+    assert lb['loss'] == pytest.approx(la['loss'], rel=0.05)
+    # one step at a given point of the schedule against the oracle at that truncation
+    r = rb
+    g0 = 37 if decay == 'linear' else 5                      # a step where the schedule is still well above its final value
+    r.global_step = g0
+    r._sync_trunc_step()
+    batch = next(r.data_loader)
+    t_rand = torch.rand(batch.shape[0], 128, device='cuda')
+    r.synchronize_parameters()
+    b = r._forward_backward(batch, t_rand=t_rand)
+    torch.cuda.synchronize()
+    P = {k: v.detach().cpu().clone() for k, v in r.models['model'].state_dict().items()}
+    P['embeddings'] = r.models['embed_fn'].embeddings.detach().cpu().clone()
+    P['offsets'] = r.models['embed_fn'].offsets.cpu().numpy()
+    P['S'] = float(np.log2(r.models['embed_fn'].per_level_scale)); P['H'] = 16
+    P['pose_data'] = r.models['pose_array'].data.detach().cpu().clone()
+    P['feature_data'] = None
+    ref = O.forward_step(P, batch.cpu(), r.c2w_array.cpu(), r.octree_m.occ.cpu().numpy(), r.cfg, global_step=g0, half=True, z_vals=b['z_vals'].cpu())
+    assert float(b['losses'][0]) == pytest.approx(float(ref['loss'].detach()), rel=5e-3)
+    # the ray march read the same scalar: the around-depth samples span depth -/+ the truncation OF THAT STEP, wider than the final one
+    tr37, tr_end = r.get_truncation(g0), r.get_truncation(r.cfg['n_step'])
+    ok = (batch[:, 6] >= r.cfg['near'] * r.cfg['sc_factor']) & (batch[:, 6] <= r.cfg['far'] * r.cfg['sc_factor'])
+    dz = (b['z_vals'][ok][:, 64:] - batch[ok, 6:7]).abs()
+    assert float(dz.max()) <= tr37 * (1 + 1e-5) and float(dz.max()) > 1.5 * tr_end, (float(dz.max()), tr37, tr_end)
+
 def test_pose_regulariser_follows_the_loss_scale():
     """pose_reg_weight > 0 under AMP: the regulariser's gradient is added to the (loss-scaled) pose gradient buffer multiplied by the
     loss scale, so that the single unscale inside nof_adam_step recovers d/dpose [pose_reg_weight * ||data[1:]||] (nerf_runner.py:748-758)."""
