@@ -148,7 +148,8 @@ class NerfRunner:
         if self.cfg['use_octree']:
             self.build_octree()
         else:
-            raise NotImplementedError('use_octree: 0 — the shipped configs always sample through the occupancy structure')
+            raise NotImplementedError('use_octree: 0 — the shipped configs always sample through the occupancy structure, and the reference\'s own '
+                                      'render_rays calls octree_m.ray_trace unconditionally (nerf_runner.py:1059)')
         self.create_nerf()
         self.create_optimizer()
         self.amp_scaler = GradScalerState(self.cfg['amp'], self.device)
