@@ -619,7 +619,8 @@ class NerfRunner:
         learning rates, loss scale, Adam step, RNG tick and the batch cursor live in device memory."""
         static = self._batch_static
         # capture stream = high priority: in the deferred mode its latency-bound kernels (prologue, ray march) run next to
-        # the table's Adam pass (normal-priority side stream) and must get SM slots as that kernel's CTAs retire
+        # the table's Adam pass (normal-priority side stream) and must get SM slots as that kernel's CTAs retire (measured at C2: 0.273 ms
+        # per step like this; 0.284-0.285 with the priorities equal or swapped)
         side = torch.cuda.Stream(priority=-1 if self._defer else 0)
         side.wait_stream(torch.cuda.current_stream())
         graph = torch.cuda.CUDAGraph()
