@@ -156,3 +156,29 @@ def test_ray_walk_as_merge_of_axis_crossings_is_bit_identical():
         b = O.ray_trace_intervals_merge(occ, o, d, i_max=a.shape[1])
         np.testing.assert_array_equal(a, b)
         assert (a[:, 0, 0] != 0).sum() > N // 2
+
+
+def test_reference_shims_reimport_once_the_extensions_are_there():
+    """tests/golden/ref_shims.import_reference: the CPU-side golden tests import the reference WITHOUT its CUDA extensions (its
+    `from mycuda import common` then fails silently); a later import WITH them (oracle/ref_train_loop.py on the GPU box) has to
+    produce fresh modules that see the extensions, or the reference's train_loop dies on `common` mid-suite."""
+    import importlib.util
+    import sys
+    import types
+    ref_dir = '/root/reference' if os.path.isdir('/root/reference') else os.path.join(REPO, 'oracle', '_ref', 'py')
+    if not os.path.exists(os.path.join(ref_dir, 'nerf_runner.py')):
+        pytest.skip('reference sources not present')
+    sys.path.insert(0, os.path.join(REPO, 'tests', 'golden'))
+    import ref_shims
+    saved = {k: sys.modules.get(k) for k in ('Utils', 'nerf_helpers', 'nerf_runner', 'mycuda', 'mycuda.common', 'gridencoder')}
+    try:
+        _, nr_plain, _ = ref_shims.import_reference(ref_dir)
+        fake_c, fake_g = types.ModuleType('common_fake'), types.ModuleType('gridencoder_fake')
+        _, nr_ext, _ = ref_shims.import_reference(ref_dir, mycuda_common=fake_c, mycuda_gridencoder=fake_g)
+        assert nr_ext is not nr_plain and nr_ext.common is fake_c
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
