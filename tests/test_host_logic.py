@@ -182,3 +182,36 @@ def test_reference_shims_reimport_once_the_extensions_are_there():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_device_cursor_protocol_walks_the_same_batches_as_the_per_step_loader():
+    """DataLoader.reserve / consumed (what NerfRunner.train_steps drives: k batches read at a device cursor by one CUDA graph) against
+    next_ids() (the reference's per-step protocol, nerf_runner.py:90-107): same permutation, same batch boundaries, same reshuffle points —
+    including the reference's rule that the last batch of an epoch is dropped when `pos + batch_size < len(ids)` fails."""
+    from bundlesdf_b200.nerf_runner import DataLoader, set_seed
+    rays = torch.arange(1003 * 12, dtype=torch.float32).reshape(1003, 12)        # 1003 rays, batches of 100: 10 per epoch, 3 rays dropped
+    set_seed(5)
+    a = DataLoader(rays, 100)
+    ids_a = []
+    for _ in range(37):
+        a.next_ids()
+        ids_a.append(a.batch_ray_ids.clone())
+    set_seed(5)
+    b = DataLoader(rays, 100)
+    ids_b, want = [], [4, 4, 10, 1, 7, 10, 1]                # block lengths a caller may ask for, crossing epoch boundaries
+    done = 0
+    while done < 37:
+        k = b.reserve(min(want[len(ids_b) % len(want)], 37 - done))
+        assert k >= 1
+        assert int(b.cursor_dev.item()) == b.pos
+        for j in range(k):                                   # what the k prologues of the graph read at the device cursor
+            cur = int(b.cursor_dev.item())
+            ids_b.append(b.ids_dev[cur: cur + 100].clone())
+            b.cursor_dev += 100                              # nof_step_prologue advances the cursor when its last block retires
+        b.consumed(k)
+        assert torch.equal(b.batch_ray_ids, ids_b[-1])
+        done += k
+    assert len(ids_b) >= 37
+    for x, y in zip(ids_a, ids_b[:37]):
+        assert torch.equal(x, y)
+    assert a.pos == b.pos
