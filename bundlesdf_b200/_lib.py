@@ -105,10 +105,13 @@ def check(rc, what=''):
         raise NofError(f'{what} failed (code {rc}): {msg}')
 
 
-def ptr(t):
-    """Device pointer of a tensor (None -> NULL). The tensor must be CUDA + contiguous."""
+def ptr(t, pinned_ok=False):
+    """Device pointer of a tensor (None -> NULL). The tensor must be CUDA + contiguous; with pinned_ok a PINNED host tensor is accepted
+    too (page-locked memory is device-addressable under unified addressing: the kernel reads / writes it across PCIe)."""
     if t is None:
         return None
+    if pinned_ok and not t.is_cuda and t.is_pinned() and t.is_contiguous():
+        return t.data_ptr()
     if not t.is_cuda:
         raise NofError('libnof_sm100 needs CUDA tensors: there is no CPU fallback for the Neural-Object-Field hot path')
     if not t.is_contiguous():

@@ -479,7 +479,7 @@ class NerfRunner:
         self._step_buf = b
         return b
 
-    def _forward_backward(self, batch, t_rand=None, taps=None, before_fused=None, gather=False, after_fused=None):
+    def _forward_backward(self, batch, t_rand=None, taps=None, before_fused=None, gather=False, after_fused=None, gather_src=None):
         """Launches the step prologue (pose correction of all frames; with `gather` also the batch gather from the ray pool at the
         data loader's device cursor, into `batch`), the ray march and the fused forward+loss+backward for `batch` [N,12].
         Gradients accumulate into the flat grad buffers (scaled by the loss scale); nothing synchronises."""
@@ -493,9 +493,10 @@ class NerfRunner:
         dl = self.data_loader
         ts = self._trunc_schedule()
         tp = ts['out'] if ts is not None else None
+        gsrc = gather_src if gather_src is not None else (self.rays, dl.ids_dev, dl.cursor_dev)   # (pool, row ids, device cursor)
         ops.step_prologue(pa.data.data if pa is not None else None, self.c2w_array, b['tf'], cfg['max_trans'] * sc, cfg['max_rot'],
-                          pool=(self.rays if gather else None), ids=(dl.ids_dev if gather else None), batch=batch,
-                          cursor=(dl.cursor_dev if gather else None), tick=self.march_tick, done=self._done_ticket,
+                          pool=(gsrc[0] if gather else None), ids=(gsrc[1] if gather else None), batch=batch,
+                          cursor=(gsrc[2] if gather else None), tick=self.march_tick, done=self._done_ticket,
                           trunc_table=(ts['table'] if ts else None), gstep=(ts['gstep'] if ts else None), trunc_out=tp)
         ops.ray_march(batch, b['tf'], self.octree_m.occ_bits, self.octree_m.level, cfg['N_samples'], cfg['N_samples_around_depth'], trunc,
                       cfg['near'] * sc, cfg['far'] * sc, cfg['neg_trunc_ratio'], t_rand=t_rand, perturb=bool(cfg.get('perturb', 1)),
@@ -561,7 +562,7 @@ class NerfRunner:
             torch.cuda.current_stream().wait_stream(self._table_stream)
         self._table_pending = False
 
-    def _step(self, batch, t_rand=None, gather=False, overlap=False, wait_before_fused=None, record_after_fused=None):
+    def _step(self, batch, t_rand=None, gather=False, overlap=False, wait_before_fused=None, record_after_fused=None, gather_src=None):
         """Forward, backward and optimizer of one step on the current stream (also what the CUDA graphs capture).
 
         cfg['defer_table_update']: the table's Adam pass (310 MB of HBM traffic at C2, the only part of the step that is bandwidth-bound)
@@ -573,7 +574,7 @@ class NerfRunner:
                          placement that overlaps across a graph boundary (single-step graphs, last step of a block)."""
         main = torch.cuda.current_stream()
         if not self._defer:
-            b = self._forward_backward(batch, t_rand=t_rand, gather=gather,
+            b = self._forward_backward(batch, t_rand=t_rand, gather=gather, gather_src=gather_src,
                                        before_fused=(lambda: main.wait_event(wait_before_fused)) if wait_before_fused is not None else None,
                                        after_fused=(lambda: record_after_fused.record(main)) if record_after_fused is not None else None)
             self._optimizer_step()
@@ -600,7 +601,7 @@ class NerfRunner:
                 with torch.cuda.stream(side):
                     self._adam_shared('table', lr_ptr=self.lr_dev[:1].data_ptr())
 
-        b = self._forward_backward(batch, t_rand=t_rand, before_fused=join, gather=gather, after_fused=fork)
+        b = self._forward_backward(batch, t_rand=t_rand, before_fused=join, gather=gather, after_fused=fork, gather_src=gather_src)
         self._adam_shared('small')
         self._table_pending = 'inflight' if overlap else 'deferred'
         return b
@@ -679,8 +680,8 @@ class NerfRunner:
 
         host_pool: a pinned CPU copy of the ray pool [P,12] (the reference keeps its pool on the host, nerf_runner.py:431; also the way to
         train on a pool that does not fit next to the model in HBM). Every step's batch is then gathered on the HOST, in the data loader's
-        order, and crosses PCIe inside the step's graph (one H2D copy node per step, running under the previous step's kernels); every
-        step's loss terms come back through a D2H node and are handed out by collect_host_losses()."""
+        order, into a pinned staging block that the step's prologue kernel reads directly across PCIe (N*48 bytes per step); every
+        step's loss terms are written back to pinned host memory by a kernel and handed out by collect_host_losses()."""
         K = max(1, int(self.cfg.get('graph_block_steps', 10)))
         N = self.cfg['N_rand']
         dl = self.data_loader
@@ -729,8 +730,10 @@ class NerfRunner:
         h = self._host
         if h is None or h['K'] != K or h['N'] != N:
             h = dict(K=K, N=N, slot=0, stage=[torch.empty(K, N, 12).pin_memory() for _ in range(2)],
-                     loss=[torch.zeros(K, 8).pin_memory() for _ in range(2)], dev=[torch.empty(N, 12, device=self.device) for _ in range(2)],
-                     ev=[None, None], meta=[None, None], staged=[None, None], up=torch.cuda.Stream(), down=torch.cuda.Stream(), out=[])
+                     loss=[torch.zeros(K, 8).pin_memory() for _ in range(2)],
+                     ev=[None, None], meta=[None, None], staged=[None, None], down=torch.cuda.Stream(), out=[],
+                     rows=torch.arange(K * N, dtype=torch.int64, device=self.device), cursor=torch.zeros(1, dtype=torch.int64, device=self.device),
+                     zero=torch.zeros(1, dtype=torch.int64, device=self.device))
             self._host = h
         return h
 
@@ -761,6 +764,7 @@ class NerfRunner:
         g = self._graph.get(key)
         if g is None:
             g = self._capture_host(key, k, h, slot)
+        h['cursor'].zero_()                                # the block's prologues read rows [0, N), [N, 2N), ... of the staging slot
         g['graph'].replay()
         ev = torch.cuda.Event()
         ev.record()
@@ -790,36 +794,30 @@ class NerfRunner:
         return np.concatenate([o[1] for o in out], 0) if out else np.zeros((0, 8), dtype=np.float32)
 
     def _capture_host(self, key, n_steps, h, slot):
-        """Like _capture, but every step's batch arrives by an H2D copy node from the pinned staging slot (into one of two device buffers,
-        under the previous step's kernels) and every step's losses leave by a D2H node right after its fused kernel."""
+        """Like _capture, but every step's prologue gathers its batch straight out of the PINNED staging slot (page-locked host memory is
+        device-addressable: the rows cross PCIe inside the kernel, N*48 bytes per step, no copy node and no extra launch) and every
+        step's loss terms are written to pinned host memory by a 1-row gather right after its fused kernel (32 bytes per step)."""
         self._ensure_step_buffers(h['N'])
-        stage, lossh, dev, up, down = h['stage'][slot], h['loss'][slot], h['dev'], h['up'], h['down']
+        stage, lossh, down = h['stage'][slot], h['loss'][slot], h['down']
+        static = self._static_batch(h['N'])
+        src = (stage.view(-1, 12), h['rows'], h['cursor'])
         cap = torch.cuda.Stream(priority=-1 if self._defer else 0)
         cap.wait_stream(torch.cuda.current_stream())
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=cap):
             main = torch.cuda.current_stream()
-            up.wait_stream(main)                            # uploads and downloads on their own streams: an upload queued behind a download
-            down.wait_stream(main)                          # would wait for that step's fused kernel and land on the next step's critical path
-            ev_up = [torch.cuda.Event() for _ in range(n_steps)]
+            down.wait_stream(main)
             ev_fused = [torch.cuda.Event() for _ in range(n_steps)]
             ev_loss = [torch.cuda.Event() for _ in range(n_steps)]
             for i in range(n_steps):
-                with torch.cuda.stream(up):
-                    if i >= 2:
-                        up.wait_event(ev_fused[i - 2])       # the ray march and the fused kernel of step i-2 have read this buffer
-                    dev[i % 2].copy_(stage[i], non_blocking=True)
-                    ev_up[i].record(up)
-                main.wait_event(ev_up[i])
-                self._step(dev[i % 2], gather=False, overlap=(i + 1 < n_steps), wait_before_fused=(ev_loss[i - 1] if i else None),
+                self._step(static, gather=True, gather_src=src, overlap=(i + 1 < n_steps), wait_before_fused=(ev_loss[i - 1] if i else None),
                            record_after_fused=ev_fused[i])
-                with torch.cuda.stream(down):
+                with torch.cuda.stream(down):               # off the step's critical path: the next operand pack (which zeroes the losses) waits for it
                     down.wait_event(ev_fused[i])
-                    lossh[i].copy_(self._step_buf['losses'], non_blocking=True)   # before the next step's operand pack zeroes them
+                    ops.gather_rays(self._step_buf['losses'].view(1, 8), h['zero'], out=lossh[i:i + 1])
                     ev_loss[i].record(down)
-            main.wait_stream(up)
             main.wait_stream(down)
-        self._graph[key] = g = dict(graph=graph, batch=dev[0], buf=self._step_buf)
+        self._graph[key] = g = dict(graph=graph, batch=static, buf=self._step_buf)
         return g
 
     def train_loop(self, batch, t_rand=None):

@@ -65,7 +65,7 @@ def step_prologue(pose_data, c2w, tf, max_trans, max_rot_deg, pool=None, ids=Non
     """nof_step_prologue: [batch gather at the device cursor] + pose correction of all frames + counter bumps, one launch."""
     lib = _lib.load()
     F = c2w.shape[0]
-    p = NofPrologue(_lib.ptr(pool), _lib.ptr(ids), int(ids.shape[0]) if ids is not None else 0, _lib.ptr(batch),
+    p = NofPrologue(_lib.ptr(pool, pinned_ok=True), _lib.ptr(ids), int(ids.shape[0]) if ids is not None else 0, _lib.ptr(batch),
                     int(batch.shape[0]) if batch is not None else 0, int(batch.shape[1]) if batch is not None else 0, _lib.ptr(cursor),
                     _lib.ptr(pose_data), _lib.ptr(c2w), _lib.ptr(tf), F, float(max_trans), float(max_rot_deg), _lib.ptr(tick), _lib.ptr(done),
                     _lib.ptr(trunc_table), int(trunc_table.shape[0]) if trunc_table is not None else 0, _lib.ptr(gstep), _lib.ptr(trunc_out))
@@ -77,7 +77,7 @@ def gather_rays(pool, ids, out=None):
     lib = _lib.load()
     N, D = ids.shape[0], pool.shape[1]
     batch = out if out is not None else torch.empty(N, D, device=pool.device, dtype=torch.float32)
-    _lib.check(lib.nof_gather_rays(_lib.ptr(pool), _lib.ptr(ids), _lib.ptr(batch), N, D, _lib.stream()), 'nof_gather_rays')
+    _lib.check(lib.nof_gather_rays(_lib.ptr(pool, pinned_ok=True), _lib.ptr(ids), _lib.ptr(batch, pinned_ok=True), N, D, _lib.stream()), 'nof_gather_rays')
     return batch
 
 

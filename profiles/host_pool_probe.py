@@ -1,6 +1,7 @@
 """train_steps(host_pool=...) against the device-resident pool: 20-step blocks at C2 (sync on both sides of every block, like bench.py), plus the
-host-side staging time alone. Measured on the B200: device pool 5.45 ms, host pool 6.52 ms per 20 steps (staging 10 batches: 0.27 ms, hidden);
-with the H2D nodes removed (stale batches) 4.83 ms, with upload and download sharing one stream 6.74 ms."""
+host-side staging time alone. Measured on the B200: device pool 5.42 ms per 20 steps; host pool 6.45 ms with the prologue reading the pinned
+staging block directly (shipped), 6.52 ms with one H2D + one D2H copy node per step on separate streams, 6.74 ms with both on one stream;
+staging 10 batches on the host 0.27 ms (overlapped). The per-step public loop (train_loop + H2D/D2H, bench.py's e2e) is at 6.3 ms."""
 import os, sys, time
 import numpy as np
 import torch
