@@ -215,3 +215,26 @@ def test_device_cursor_protocol_walks_the_same_batches_as_the_per_step_loader():
     for x, y in zip(ids_a, ids_b[:37]):
         assert torch.equal(x, y)
     assert a.pos == b.pos
+
+
+@pytest.mark.parametrize('decay', ['', 'linear', 'exp'])
+def test_truncation_schedule_matches_the_references_own_method(decay):
+    """get_truncation (nerf_runner.py:663-676): the product's host formula (which also fills the device table of the annealed schedule) and the
+    oracle's, against the reference's own NerfRunner.get_truncation called on a stand-in self — every step of a 500-step run, bit for bit."""
+    import sys
+    import types
+    ref_dir = '/root/reference' if os.path.isdir('/root/reference') else os.path.join(REPO, 'oracle', '_ref', 'py')
+    if not os.path.exists(os.path.join(ref_dir, 'nerf_runner.py')):
+        pytest.skip('reference sources not present')
+    sys.path.insert(0, os.path.join(REPO, 'tests', 'golden'))
+    import ref_shims
+    from bundlesdf_b200.nerf_runner import NerfRunner
+    from oracle import nof_oracle as O
+    _, nr, _ = ref_shims.import_reference(ref_dir)
+    cfg = dict(trunc_decay_type=decay, trunc_start=0.03, trunc=0.01, n_step=500, sc_factor=3.7)
+    for g in list(range(0, 40)) + [123, 124, 125, 126, 250, 499, 500, 501]:
+        me = types.SimpleNamespace(cfg=cfg, global_step=g)
+        want = nr.NerfRunner.get_truncation(me)
+        assert NerfRunner.get_truncation(me) == want
+        assert NerfRunner.get_truncation(me, step=g) == want
+        assert O.get_truncation(cfg, g) == want
